@@ -1,0 +1,92 @@
+/*
+ * uvrt_host.h -- flat C view of the host-side drop-in classes (Mesh, BVH, RayTracer in
+ * small-project-uv-robot-ray-tracer_b200/host/, same public surface as the reference's
+ * mesh.h / bvh.h / raytracer.h) for callers that cannot include C++ headers: the Python
+ * tests and bench.py (ctypes).  C++ callers use the classes directly.
+ *
+ * A uvrt_sim owns one Tmpl8::Mesh and one Tmpl8::RayTracer, i.e. what MyApp holds in the
+ * reference (myapp.h).  Every function returns 0 or a negative uvrt_status (uvrt.h).
+ */
+#ifndef UVRT_HOST_H
+#define UVRT_HOST_H
+
+#include "uvrt.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct uvrt_sim uvrt_sim;
+
+/* Mirror of RayTracer's tunable / progress fields (raytracer.h:28-56 of the reference). */
+typedef struct uvrt_sim_params {
+    int photonCount;       /* aantal_fotonen */
+    int maxIterations;     /* aantal_iteraties */
+    float lightIntensity;  /* lamp_sterkte */
+    float minDosage;       /* minimale_dosis */
+    float minPower;        /* minimale_bestralingssterkte */
+    float lightLength;     /* lamp_lengte */
+    float lightHeight;     /* lamp_hoogte */
+    int viewMode;          /* 0 dosage, 1 maxpower, 2 texture */
+    int thresholdView;
+    /* read-only progress */
+    int photonsPerLight;
+    int currIterations;
+    int photonMapSize;
+    uint32_t seedState;
+    int finishedComputation;
+} uvrt_sim_params;
+
+/* assetRoot: directory holding rooms/ and positions/ (NULL or "": working directory, as in the
+ * reference).  device: CUDA ordinal used by Init. */
+int uvrt_sim_create(uvrt_sim** out, const char* assetRoot, int device);
+void uvrt_sim_destroy(uvrt_sim* sim);
+const char* uvrt_sim_last_error(const uvrt_sim* sim);
+
+/* Mesh::LoadMesh (mesh.cpp:5-98): rooms/<modelFile>.glb -> Tri[], floor height, BVH.  CPU only. */
+int uvrt_sim_load_mesh(uvrt_sim* sim, const char* modelFile);
+/* Mesh from caller-supplied triangles (n x 64 B, reference layout); builds the BVH.  CPU only. */
+int uvrt_sim_set_triangles(uvrt_sim* sim, const void* tris, int n);
+int uvrt_sim_mesh_info(const uvrt_sim* sim, int* triangleCount, float* floorHeight, unsigned* nodesUsed);
+/* Borrowed pointers into the mesh: Tri[triangleCount], BVHNode[nodesUsed], triIdx[triangleCount]. */
+int uvrt_sim_mesh_data(const uvrt_sim* sim, const void** tris, const void** nodes, const unsigned** triIdx);
+
+/* RayTracer::LoadRoute / SaveRoute (raytracer.cpp:233-300): positions/<name>.xml.  CPU only. */
+int uvrt_sim_load_route(uvrt_sim* sim, const char* name);
+int uvrt_sim_save_route(uvrt_sim* sim, const char* name);
+int uvrt_sim_get_params(const uvrt_sim* sim, uvrt_sim_params* p);
+int uvrt_sim_set_params(uvrt_sim* sim, const uvrt_sim_params* p);   /* writable fields only */
+/* lightPositions as (x, y, duration) triples */
+int uvrt_sim_get_positions(const uvrt_sim* sim, float* xyd, int capacity, int* count);
+int uvrt_sim_set_positions(uvrt_sim* sim, const float* xyd, int count);
+
+/* RayTracer::Init (raytracer.cpp:12-59): loads positions/<routeName>.xml (NULL: keep the current
+ * route and parameters), creates the backend context, uploads the scene.  Needs a GPU. */
+int uvrt_sim_init(uvrt_sim* sim, const char* routeName);
+int uvrt_sim_reset_dosage_map(uvrt_sim* sim);            /* RayTracer::ResetDosageMap */
+int uvrt_sim_compute_dosage_map(uvrt_sim* sim);          /* RayTracer::ComputeDosageMap */
+int uvrt_sim_compute_single(uvrt_sim* sim, float x, float y, float duration, int photons, int triangleCount);
+int uvrt_sim_shade(uvrt_sim* sim);                       /* RayTracer::Shade */
+/* One frame of MyApp::Tick (myapp.cpp:156-175): ComputeDosageMap + Shade + currIterations++ +
+ * device sync.  *finished = 1 once currIterations >= maxIterations (nothing is computed then). */
+int uvrt_sim_tick(uvrt_sim* sim, int* finished);
+/* ResetDosageMap, then Tick until finished, then (sharded runs) Reduce + Shade.  The dose map is
+ * copied into dose[0..triangleCount) when dose != NULL. */
+int uvrt_sim_run(uvrt_sim* sim, float* dose, int capacity);
+int uvrt_sim_calibrate(uvrt_sim* sim, float measurePower, float measureHeight, float measureDist, float* calibratedPower);
+int uvrt_sim_read_dose(uvrt_sim* sim, float* dst, int capacity);
+/* Work sharing over ranks (launch k goes to rank k % count) and the final cross-rank reduction. */
+int uvrt_sim_set_shard(uvrt_sim* sim, int rank, int count);
+int uvrt_sim_reduce(uvrt_sim* sim);
+/* The backend context behind the RayTracer (valid after uvrt_sim_init), for uvrt_read & co. */
+uvrt_ctx* uvrt_sim_ctx(uvrt_sim* sim);
+int64_t uvrt_sim_rays_traced(const uvrt_sim* sim);
+
+/* The BVH builder on its own (bvh.cpp): tris is n x 64 B (centroids are written), nodesOut holds
+ * nodeCapacity >= 2n+64 slots of 32 B, triIdxOut n u32.  CPU only. */
+int uvrt_host_build_bvh(void* tris, int n, void* nodesOut, int nodeCapacity, unsigned* triIdxOut, unsigned* nodesUsed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UVRT_HOST_H */

@@ -1,0 +1,844 @@
+// uvrt_capi.cu -- the C ABI of include/uvrt.h over the kernels of uvrt_kernels.cuh.
+//
+// Replaces the reference's OpenCL wrapper layer (template/template.cpp:1039-1573) for the one
+// path RayTracer drives (raytracer.cpp:12-143).  No torch, no C++ types in the interface.
+#include "../../include/uvrt.h"
+#include "uvrt_kernels.cuh"
+
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace uvrt;
+
+// ---- NCCL, bound at run time so that libuvrt.so loads on machines without it -------------------
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { kNcclSuccess = 0 };
+enum { kNcclInt32 = 2, kNcclFloat64 = 8 };
+enum { kNcclSum = 0, kNcclMax = 2 };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string why;
+    bool ok = false;
+};
+NcclApi g_nccl;
+
+bool nccl_load()
+{
+    if (g_nccl.ok) return true;
+    if (g_nccl.lib == nullptr) {
+        const char* env = getenv("UVRT_NCCL_LIB");
+        const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n || !*n) continue;
+            g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.lib) break;
+        }
+        if (!g_nccl.lib) {
+            g_nccl.why = "libnccl.so.2 not found (set UVRT_NCCL_LIB)";
+            return false;
+        }
+    }
+#define UVRT_SYM(field, name)                                                   \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                         \
+    if (!g_nccl.field) { g_nccl.why = std::string("missing symbol ") + name; return false; }
+    UVRT_SYM(GetUniqueId, "ncclGetUniqueId")
+    UVRT_SYM(CommInitRank, "ncclCommInitRank")
+    UVRT_SYM(CommDestroy, "ncclCommDestroy")
+    UVRT_SYM(AllReduce, "ncclAllReduce")
+    UVRT_SYM(GroupStart, "ncclGroupStart")
+    UVRT_SYM(GroupEnd, "ncclGroupEnd")
+    UVRT_SYM(GetErrorString, "ncclGetErrorString")
+#undef UVRT_SYM
+    g_nccl.ok = true;
+    return true;
+}
+
+thread_local std::string g_create_error;
+} // namespace
+
+struct TimedLaunch {
+    cudaEvent_t start, stop;
+    int stage;
+};
+
+struct uvrt_ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    std::string err;
+
+    // scene (device layout, DESIGN.md "Data layout in HBM")
+    int nTris = 0;
+    int nPairs = 0, nLeaves = 0, depth = 0;
+    uint32_t rootRef = 0;
+    int sceneTame = 0;
+    float4* dPairs = nullptr;   // nPairs x 4 float4
+    float4* dWtris = nullptr;   // nTris  x 3 float4 (leaf order)
+    float4* dVerts = nullptr;   // nTris  x 4 float4 (reference order and layout)
+    // per-triangle state (raytracer.h:54-55)
+    int* dCounts = nullptr;
+    double* dSum = nullptr;
+    double* dMax = nullptr;
+    float* dDose = nullptr;
+    float* dColor = nullptr;
+    // rays
+    float4* dRays = nullptr;
+    long long rayCap = 0;
+    long long lastRays = 0;
+    unsigned int* dQueue = nullptr;      // persistent-kernel work counter
+    uint32_t* dSeeds = nullptr;
+    float* dSeedPos = nullptr;
+    int seedCap = 0;
+    // pinned staging for the scene upload
+    void* hStage = nullptr;
+    size_t hStageBytes = 0;
+
+    // options
+    int extendVariant = -1;   // -1: default
+    int stageTiming = 0;
+    int histMode = 0;
+    int blocksPerSm = 0;      // 0: default for the variant
+
+    // measurement
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> freeEvents;
+    cudaEvent_t marks[16] = {};
+    int64_t launches = 0;
+
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, nRanks = 1;
+};
+
+namespace {
+
+int fail(uvrt_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? UVRT_ERR_NO_MEMORY : UVRT_ERR_CUDA, \
+                        "%s failed: %s", #call, cudaGetErrorString(e_));                      \
+    } while (0)
+
+struct Bind {
+    explicit Bind(uvrt_ctx* c) { cudaGetDevice(&prev); if (prev != c->device) cudaSetDevice(c->device); dev = c->device; }
+    ~Bind() { if (prev != dev && prev >= 0) cudaSetDevice(prev); }
+    int prev = -1, dev = -1;
+};
+
+cudaEvent_t get_event(uvrt_ctx* ctx)
+{
+    if (!ctx->freeEvents.empty()) {
+        cudaEvent_t e = ctx->freeEvents.back();
+        ctx->freeEvents.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct StageTimer {
+    uvrt_ctx* ctx;
+    TimedLaunch t{};
+    bool on;
+    StageTimer(uvrt_ctx* c, int stage) : ctx(c), on(c->stageTiming != 0)
+    {
+        if (!on) return;
+        t.stage = stage;
+        t.start = get_event(c);
+        t.stop = get_event(c);
+        cudaEventRecord(t.start, c->stream);
+    }
+    ~StageTimer()
+    {
+        if (!on) return;
+        cudaEventRecord(t.stop, ctx->stream);
+        ctx->timed.push_back(t);
+    }
+};
+
+template <typename T>
+int dev_alloc(uvrt_ctx* ctx, T** p, size_t count)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) return UVRT_OK;
+    CK(cudaMalloc((void**)p, count * sizeof(T)));
+    return UVRT_OK;
+}
+
+int ensure_rays(uvrt_ctx* ctx, long long nRays)
+{
+    if (nRays <= ctx->rayCap) return UVRT_OK;
+    // raytracer.cpp:137 sizes the ray buffer by photonCount; here it follows the largest launch
+    long long cap = std::max<long long>(nRays, 1 << 16);
+    if (ctx->dRays) { cudaFree(ctx->dRays); ctx->dRays = nullptr; ctx->rayCap = 0; }
+    CK(cudaMalloc((void**)&ctx->dRays, (size_t)cap * 32));
+    ctx->rayCap = cap;
+    return UVRT_OK;
+}
+
+struct HostTri { float v[16]; };
+struct HostNode { float mn[3]; uint32_t leftFirst; float mx[3]; uint32_t triCount; };
+
+bool coord_tame(float v)
+{
+    float a = std::fabs(v);
+    return a == 0.0f || (a >= 9.5367431640625e-07f && a <= 1048576.0f);
+}
+
+int check_buffer(uvrt_ctx* ctx, uvrt_buffer what, void** ptr, size_t* bytes)
+{
+    size_t n = (size_t)ctx->nTris;
+    switch (what) {
+    case UVRT_BUF_RAYS: *ptr = ctx->dRays; *bytes = (size_t)ctx->rayCap * 32; return UVRT_OK;
+    case UVRT_BUF_COUNTS: *ptr = ctx->dCounts; *bytes = n * 4; return UVRT_OK;
+    case UVRT_BUF_SUM: *ptr = ctx->dSum; *bytes = n * 8; return UVRT_OK;
+    case UVRT_BUF_MAX: *ptr = ctx->dMax; *bytes = n * 8; return UVRT_OK;
+    case UVRT_BUF_DOSE: *ptr = ctx->dDose; *bytes = n * 4; return UVRT_OK;
+    case UVRT_BUF_COLOR: *ptr = ctx->dColor; *bytes = n * 36; return UVRT_OK;
+    }
+    return fail(ctx, UVRT_ERR_INVALID, "unknown buffer id %d", (int)what);
+}
+
+inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// ---- extend dispatch ---------------------------------------------------------------------------
+// Variant ids (uvrt_set_option "extend_variant"):
+//   0  simple / IEEE division            (literal restatement)
+//   1  simple / Markstein two-step
+//   2  simple / Markstein one-step
+//   10 + 3*k + d  persistent, K = {1, 2, 4, 8, inf}[k], d = {IEEE, M2, M1}
+constexpr int kStack = 64;
+constexpr int kDefaultVariant = 1;
+
+template <int DIV>
+void launch_simple(uvrt_ctx* ctx, long long nRays)
+{
+    k_extend_simple<DIV, kStack><<<grid_for(nRays, 128), 128, 0, ctx->stream>>>(
+        ctx->dCounts, ctx->dWtris, ctx->dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame);
+}
+
+template <int DIV, int K, int HIST>
+void launch_persist(uvrt_ctx* ctx, long long nRays)
+{
+    constexpr int THREADS = 128;
+    constexpr int MINB = 4;
+    auto kern = k_extend_persist<DIV, kStack, K, 24, HIST, THREADS, MINB>;
+    int perSm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, THREADS, 0);
+    if (perSm < 1) perSm = 1;
+    if (ctx->blocksPerSm > 0) perSm = std::min(perSm, ctx->blocksPerSm);
+    long long blocks = (long long)perSm * ctx->prop.multiProcessorCount;
+    long long needed = (nRays + THREADS - 1) / THREADS;
+    if (blocks > needed) blocks = needed;
+    cudaMemsetAsync(ctx->dQueue, 0, sizeof(unsigned int), ctx->stream);
+    kern<<<(unsigned)blocks, THREADS, 0, ctx->stream>>>(ctx->dCounts, ctx->dWtris, ctx->dRays, ctx->dPairs,
+                                                        ctx->rootRef, (uint32_t)nRays, ctx->sceneTame, ctx->dQueue);
+}
+
+template <int DIV, int K>
+void launch_persist_h(uvrt_ctx* ctx, long long nRays)
+{
+    if (ctx->histMode) launch_persist<DIV, K, 1>(ctx, nRays);
+    else launch_persist<DIV, K, 0>(ctx, nRays);
+}
+
+template <int K>
+void launch_persist_d(uvrt_ctx* ctx, long long nRays, int d)
+{
+    if (d == 0) launch_persist_h<DIV_IEEE, K>(ctx, nRays);
+    else if (d == 1) launch_persist_h<DIV_MARKSTEIN2, K>(ctx, nRays);
+    else launch_persist_h<DIV_MARKSTEIN1, K>(ctx, nRays);
+}
+
+int launch_extend(uvrt_ctx* ctx, long long nRays)
+{
+    int v = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
+    if (v == 0) launch_simple<DIV_IEEE>(ctx, nRays);
+    else if (v == 1) launch_simple<DIV_MARKSTEIN2>(ctx, nRays);
+    else if (v == 2) launch_simple<DIV_MARKSTEIN1>(ctx, nRays);
+    else if (v >= 10 && v < 25) {
+        int k = (v - 10) / 3, d = (v - 10) % 3;
+        switch (k) {
+        case 0: launch_persist_d<1>(ctx, nRays, d); break;
+        case 1: launch_persist_d<2>(ctx, nRays, d); break;
+        case 2: launch_persist_d<4>(ctx, nRays, d); break;
+        case 3: launch_persist_d<8>(ctx, nRays, d); break;
+        default: launch_persist_d<(1 << 30)>(ctx, nRays, d); break;
+        }
+    } else
+        return fail(ctx, UVRT_ERR_INVALID, "unknown extend_variant %d", v);
+    ctx->launches++;
+    return UVRT_OK;
+}
+
+} // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* uvrt_version(void) { return "uvrt-b200 0.1 (sm_100a)"; }
+
+int uvrt_device_count(int* count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (count) *count = (e == cudaSuccess) ? n : 0;
+    if (e != cudaSuccess) return fail(nullptr, UVRT_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return UVRT_OK;
+}
+
+int uvrt_create(uvrt_ctx** out, int device)
+{
+    if (!out) return fail(nullptr, UVRT_ERR_INVALID, "uvrt_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, UVRT_ERR_NO_DEVICE, "no usable CUDA device (%s); libuvrt has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(nullptr, UVRT_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    uvrt_ctx* ctx = new (std::nothrow) uvrt_ctx();
+    if (!ctx) return fail(nullptr, UVRT_ERR_NO_MEMORY, "out of host memory");
+    ctx->device = device;
+    cudaGetDeviceProperties(&ctx->prop, device);
+    if (ctx->prop.major < 10) {
+        int rc = fail(nullptr, UVRT_ERR_NO_DEVICE, "device %d is sm_%d%d; this build only carries sm_100a code", device,
+                      ctx->prop.major, ctx->prop.minor);
+        delete ctx;
+        return rc;
+    }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->dQueue, 256);
+    for (int i = 0; i < 16 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->marks[i]);
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        int rc = fail(nullptr, UVRT_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return UVRT_OK;
+}
+
+void uvrt_destroy(uvrt_ctx* ctx)
+{
+    if (!ctx) return;
+    Bind b(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+    void* ptrs[] = {ctx->dPairs, ctx->dWtris, ctx->dVerts, ctx->dCounts, ctx->dSum, ctx->dMax, ctx->dDose,
+                    ctx->dColor, ctx->dRays, ctx->dQueue, ctx->dSeeds, ctx->dSeedPos};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (ctx->hStage) cudaFreeHost(ctx->hStage);
+    for (auto& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
+    for (auto e : ctx->freeEvents) cudaEventDestroy(e);
+    for (auto e : ctx->marks) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* uvrt_last_error(const uvrt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int uvrt_device_info(uvrt_ctx* ctx, char* dst, size_t bytes, int* smCount, int* ccMajor, int* ccMinor)
+{
+    if (!ctx) return UVRT_ERR_INVALID;
+    if (dst && bytes) snprintf(dst, bytes, "%s", ctx->prop.name);
+    if (smCount) *smCount = ctx->prop.multiProcessorCount;
+    if (ccMajor) *ccMajor = ctx->prop.major;
+    if (ccMinor) *ccMinor = ctx->prop.minor;
+    return UVRT_OK;
+}
+
+int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* nodesV, int nNodes,
+                      const uint32_t* triIdx)
+{
+    if (!ctx) return UVRT_ERR_INVALID;
+    if (!trisV || !nodesV || !triIdx || nTris <= 0 || nNodes <= 0)
+        return fail(ctx, UVRT_ERR_INVALID, "upload_scene: null pointer or empty scene (nTris=%d nNodes=%d)", nTris, nNodes);
+    Bind b(ctx);
+    const HostTri* tris = (const HostTri*)trisV;
+    const HostNode* nodes = (const HostNode*)nodesV;
+
+    // ---- pass 1: walk the tree from the root, number inner nodes (pairs) and leaf slots -------
+    std::vector<int32_t> id(nNodes, -1);   // inner: pair index; leaf: first slot
+    std::vector<uint32_t> order;           // reachable nodes, pre-order, left child first
+    order.reserve((size_t)std::min<long long>(nNodes, 2ll * nTris));
+    struct Item { uint32_t node; int depth; };
+    std::vector<Item> stack;
+    stack.push_back({0u, 0});
+    int nPairs = 0, nLeaves = 0, depth = 0;
+    long long nSlots = 0;
+    std::vector<uint8_t> used(nTris, 0);
+    while (!stack.empty()) {
+        Item it = stack.back();
+        stack.pop_back();
+        if (it.node >= (uint32_t)nNodes)
+            return fail(ctx, UVRT_ERR_INVALID,
+                        "upload_scene: node %u is reachable but nNodes is %d (the reference's nodesUsed = 2N "
+                        "truncates its own tree; pass the full array)", it.node, nNodes);
+        if (id[it.node] != -1) return fail(ctx, UVRT_ERR_INVALID, "upload_scene: node %u reached twice", it.node);
+        const HostNode& nd = nodes[it.node];
+        depth = std::max(depth, it.depth);
+        order.push_back(it.node);
+        if (nd.triCount > 0) {
+            if ((long long)nd.leftFirst + nd.triCount > nTris)
+                return fail(ctx, UVRT_ERR_INVALID, "upload_scene: leaf %u spans triIdx[%u..%u) of %d", it.node,
+                            nd.leftFirst, nd.leftFirst + nd.triCount, nTris);
+            id[it.node] = (int32_t)nSlots;
+            for (uint32_t k = 0; k < nd.triCount; k++) {
+                uint32_t t = triIdx[nd.leftFirst + k];
+                if (t >= (uint32_t)nTris) return fail(ctx, UVRT_ERR_INVALID, "upload_scene: triIdx value %u out of range", t);
+                used[t]++;
+            }
+            nSlots += nd.triCount;
+            nLeaves++;
+        } else {
+            id[it.node] = nPairs++;
+            stack.push_back({nd.leftFirst + 1, it.depth + 1});
+            stack.push_back({nd.leftFirst, it.depth + 1});
+        }
+    }
+    if (depth + 1 > kStack)
+        return fail(ctx, UVRT_ERR_INVALID, "upload_scene: BVH depth %d exceeds the traversal stack (%d)", depth, kStack);
+
+    // ---- pass 2: fill the staging image --------------------------------------------------------
+    size_t pairBytes = (size_t)std::max(nPairs, 1) * 64, wtriBytes = (size_t)std::max<long long>(nSlots, 1) * 48,
+           vertBytes = (size_t)nTris * 64;
+    size_t total = pairBytes + wtriBytes + vertBytes;
+    if (ctx->hStageBytes < total) {
+        if (ctx->hStage) cudaFreeHost(ctx->hStage);
+        ctx->hStage = nullptr;
+        ctx->hStageBytes = 0;
+        CK(cudaMallocHost(&ctx->hStage, total));
+        ctx->hStageBytes = total;
+    }
+    float* hp = (float*)ctx->hStage;
+    float* hw = (float*)((char*)ctx->hStage + pairBytes);
+    float* hv = (float*)((char*)ctx->hStage + pairBytes + wtriBytes);
+    memset(hp, 0, pairBytes);
+    bool tame = true;
+    auto child_ref = [&](uint32_t n) -> uint32_t {
+        return nodes[n].triCount > 0 ? (kLeafFlag | (uint32_t)id[n]) : (uint32_t)id[n];
+    };
+    for (uint32_t n : order) {
+        const HostNode& nd = nodes[n];
+        if (nd.triCount > 0) {
+            for (uint32_t k = 0; k < nd.triCount; k++) {
+                uint32_t t = triIdx[nd.leftFirst + k];
+                const float* v = tris[t].v;
+                float* w = hw + ((size_t)id[n] + k) * 12;
+                w[0] = v[0]; w[1] = v[1]; w[2] = v[2];
+                uint32_t tag = t | (k + 1 == nd.triCount ? kLastFlag : 0u);
+                memcpy(&w[3], &tag, 4);
+                // edge1 = v1 - v0, edge2 = v2 - v0 (extend.cl:13): the same fp32 subtractions, hoisted
+                w[4] = v[4] - v[0]; w[5] = v[5] - v[1]; w[6] = v[6] - v[2]; w[7] = 0.0f;
+                w[8] = v[8] - v[0]; w[9] = v[9] - v[1]; w[10] = v[10] - v[2]; w[11] = 0.0f;
+            }
+        } else {
+            float* p = hp + (size_t)id[n] * 16;
+            for (int c = 0; c < 2; c++) {
+                const HostNode& ch = nodes[nd.leftFirst + c];
+                float* q = p + c * 8;
+                q[0] = ch.mn[0]; q[1] = ch.mn[1]; q[2] = ch.mn[2];
+                uint32_t ref = child_ref(nd.leftFirst + c);
+                memcpy(&q[3], &ref, 4);
+                q[4] = ch.mx[0]; q[5] = ch.mx[1]; q[6] = ch.mx[2]; q[7] = 0.0f;
+                for (int a = 0; a < 3; a++) tame = tame && coord_tame(ch.mn[a]) && coord_tame(ch.mx[a]);
+            }
+        }
+    }
+    memcpy(hv, tris, vertBytes);
+
+    // ---- device buffers -------------------------------------------------------------------------
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->dPairs, pairBytes / 16))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->dWtris, wtriBytes / 16))) return rc;
+    if (nTris != ctx->nTris) {
+        if ((rc = dev_alloc(ctx, &ctx->dVerts, (size_t)nTris * 4))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->dCounts, (size_t)nTris))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->dSum, (size_t)nTris))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->dMax, (size_t)nTris))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->dDose, (size_t)nTris))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->dColor, (size_t)nTris * 9))) return rc;
+        ctx->nTris = nTris;
+        CK(cudaMemsetAsync(ctx->dCounts, 0, (size_t)nTris * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->dSum, 0, (size_t)nTris * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->dMax, 0, (size_t)nTris * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->dDose, 0, (size_t)nTris * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->dColor, 0, (size_t)nTris * 36, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->dPairs, hp, pairBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dWtris, hw, wtriBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dVerts, hv, vertBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // the staging buffer may be reused right away
+    ctx->nPairs = nPairs;
+    ctx->nLeaves = nLeaves;
+    ctx->depth = depth;
+    ctx->sceneTame = tame ? 1 : 0;
+    ctx->rootRef = child_ref(0);
+    return UVRT_OK;
+}
+
+int uvrt_scene_info(uvrt_ctx* ctx, int* innerNodes, int* leaves, int* depth, int* stackEntries)
+{
+    if (!ctx) return UVRT_ERR_INVALID;
+    if (!ctx->nTris) return fail(ctx, UVRT_ERR_NO_SCENE, "no scene uploaded");
+    if (innerNodes) *innerNodes = ctx->nPairs;
+    if (leaves) *leaves = ctx->nLeaves;
+    if (depth) *depth = ctx->depth;
+    if (stackEntries) *stackEntries = kStack;
+    return UVRT_OK;
+}
+
+#define NEED_SCENE()                                                                       \
+    if (!ctx) return UVRT_ERR_INVALID;                                                     \
+    if (!ctx->nTris) return fail(ctx, UVRT_ERR_NO_SCENE, "%s: no scene uploaded", __func__); \
+    Bind bind_(ctx)
+
+#define CK_LAUNCH(name)                                                                    \
+    do {                                                                                   \
+        cudaError_t e_ = cudaGetLastError();                                               \
+        if (e_ != cudaSuccess) return fail(ctx, UVRT_ERR_CUDA, "%s launch failed: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+int uvrt_reset(uvrt_ctx* ctx, int resetColor)
+{
+    NEED_SCENE();
+    {
+        StageTimer t(ctx, UVRT_STAGE_RESET);
+        k_reset<<<grid_for(ctx->nTris, 256), 256, 0, ctx->stream>>>(ctx->dSum, ctx->dMax, ctx->dCounts, ctx->dColor,
+                                                                     resetColor, ctx->nTris);
+    }
+    ctx->launches++;
+    CK_LAUNCH("reset");
+    return UVRT_OK;
+}
+
+int uvrt_generate(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, int64_t firstRay, int64_t nRays,
+                  uint32_t seedIn)
+{
+    NEED_SCENE();
+    if (nRays < 0 || firstRay < 0 || nRays > 0x7fffffffll)
+        return fail(ctx, UVRT_ERR_INVALID, "generate: bad ray range first=%lld n=%lld", (long long)firstRay, (long long)nRays);
+    int rc = ensure_rays(ctx, nRays);
+    if (rc) return rc;
+    ctx->lastRays = nRays;
+    if (nRays == 0) return UVRT_OK;
+    {
+        StageTimer t(ctx, UVRT_STAGE_GENERATE);
+        k_generate<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dRays, firstRay, nRays, lx, ly, lz, lightLength, seedIn);
+    }
+    ctx->launches++;
+    CK_LAUNCH("generate");
+    return UVRT_OK;
+}
+
+int uvrt_extend(uvrt_ctx* ctx, int64_t nRays)
+{
+    NEED_SCENE();
+    if (nRays < 0 || nRays > ctx->rayCap)
+        return fail(ctx, UVRT_ERR_INVALID, "extend: nRays=%lld exceeds the ray buffer (%lld)", (long long)nRays, ctx->rayCap);
+    if (nRays == 0) return UVRT_OK;
+    int rc;
+    {
+        StageTimer t(ctx, UVRT_STAGE_EXTEND);
+        rc = launch_extend(ctx, nRays);
+    }
+    if (rc) return rc;
+    CK_LAUNCH("extend");
+    return UVRT_OK;
+}
+
+int uvrt_accumulate(uvrt_ctx* ctx, float duration)
+{
+    NEED_SCENE();
+    {
+        StageTimer t(ctx, UVRT_STAGE_ACCUMULATE);
+        k_accumulate<<<grid_for(ctx->nTris, 256), 256, 0, ctx->stream>>>(ctx->dSum, ctx->dMax, ctx->dCounts, duration, ctx->nTris);
+    }
+    ctx->launches++;
+    CK_LAUNCH("accumulate");
+    return UVRT_OK;
+}
+
+int uvrt_trace_counts(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, int64_t firstRay, int64_t nRays,
+                      uint32_t seedIn)
+{
+    int rc = uvrt_generate(ctx, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
+    if (rc) return rc;
+    return uvrt_extend(ctx, nRays);
+}
+
+int uvrt_trace(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, float duration, int64_t firstRay,
+               int64_t nRays, uint32_t seedIn)
+{
+    int rc = uvrt_trace_counts(ctx, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
+    if (rc) return rc;
+    return uvrt_accumulate(ctx, duration);
+}
+
+int uvrt_seed_chain(uvrt_ctx* ctx, const float* lightPos3, int nLaunches, float lightLength, uint32_t seedIn,
+                    uint32_t* seedsOut)
+{
+    if (!ctx) return UVRT_ERR_INVALID;
+    if (nLaunches < 0 || !seedsOut || (nLaunches > 0 && !lightPos3))
+        return fail(ctx, UVRT_ERR_INVALID, "seed_chain: bad arguments");
+    Bind b(ctx);
+    if (nLaunches + 1 > ctx->seedCap) {
+        int cap = std::max(nLaunches + 1, 256);
+        if (ctx->dSeeds) cudaFree(ctx->dSeeds);
+        if (ctx->dSeedPos) cudaFree(ctx->dSeedPos);
+        ctx->dSeeds = nullptr; ctx->dSeedPos = nullptr; ctx->seedCap = 0;
+        CK(cudaMalloc((void**)&ctx->dSeeds, (size_t)cap * 4));
+        CK(cudaMalloc((void**)&ctx->dSeedPos, (size_t)cap * 12));
+        ctx->seedCap = cap;
+    }
+    if (nLaunches > 0)
+        CK(cudaMemcpyAsync(ctx->dSeedPos, lightPos3, (size_t)nLaunches * 12, cudaMemcpyHostToDevice, ctx->stream));
+    k_seed_chain<<<1, 32, 0, ctx->stream>>>(ctx->dSeedPos, nLaunches, lightLength, seedIn, ctx->dSeeds);
+    ctx->launches++;
+    CK_LAUNCH("seed_chain");
+    CK(cudaMemcpyAsync(seedsOut, ctx->dSeeds, (size_t)(nLaunches + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return UVRT_OK;
+}
+
+int uvrt_shade(uvrt_ctx* ctx, int useMaxMap, int photonsPerLight, float scaledPower)
+{
+    NEED_SCENE();
+    {
+        StageTimer t(ctx, UVRT_STAGE_SHADE);
+        k_compute_dosage<<<grid_for(ctx->nTris, 256), 256, 0, ctx->stream>>>(useMaxMap ? ctx->dMax : ctx->dSum, ctx->dDose,
+                                                                              ctx->dVerts, photonsPerLight, scaledPower, ctx->nTris);
+    }
+    ctx->launches++;
+    CK_LAUNCH("computeDosage");
+    return UVRT_OK;
+}
+
+int uvrt_color(uvrt_ctx* ctx, float minValue, int thresholdView)
+{
+    NEED_SCENE();
+    {
+        StageTimer t(ctx, UVRT_STAGE_COLOR);
+        k_dosage_to_color<<<grid_for(ctx->nTris, 256), 256, 0, ctx->stream>>>(ctx->dDose, ctx->dColor, minValue, thresholdView, ctx->nTris);
+    }
+    ctx->launches++;
+    CK_LAUNCH("dosageToColor");
+    return UVRT_OK;
+}
+
+int uvrt_read(uvrt_ctx* ctx, uvrt_buffer what, void* dst, size_t bytes)
+{
+    NEED_SCENE();
+    void* p = nullptr;
+    size_t cap = 0;
+    int rc = check_buffer(ctx, what, &p, &cap);
+    if (rc) return rc;
+    if (!dst || bytes > cap) return fail(ctx, UVRT_ERR_INVALID, "read: %zu bytes requested, buffer %d holds %zu", bytes, (int)what, cap);
+    if (bytes) CK(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return UVRT_OK;
+}
+
+int uvrt_write(uvrt_ctx* ctx, uvrt_buffer what, const void* src, size_t bytes)
+{
+    NEED_SCENE();
+    if (what == UVRT_BUF_RAYS) {
+        int rc = ensure_rays(ctx, (long long)((bytes + 31) / 32));
+        if (rc) return rc;
+        ctx->lastRays = (long long)(bytes / 32);
+    }
+    void* p = nullptr;
+    size_t cap = 0;
+    int rc = check_buffer(ctx, what, &p, &cap);
+    if (rc) return rc;
+    if (!src || bytes > cap) return fail(ctx, UVRT_ERR_INVALID, "write: %zu bytes offered, buffer %d holds %zu", bytes, (int)what, cap);
+    if (bytes) CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return UVRT_OK;
+}
+
+int uvrt_sync(uvrt_ctx* ctx)
+{
+    if (!ctx) return UVRT_ERR_INVALID;
+    Bind b(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return UVRT_OK;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------------------
+int uvrt_comm_unique_id(void* id128)
+{
+    if (!id128) return UVRT_ERR_INVALID;
+    if (!nccl_load()) return fail(nullptr, UVRT_ERR_NCCL, "NCCL unavailable: %s", g_nccl.why.c_str());
+    ncclUniqueId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != kNcclSuccess) return fail(nullptr, UVRT_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+    memcpy(id128, &id, 128);
+    return UVRT_OK;
+}
+
+int uvrt_comm_init(uvrt_ctx* ctx, const void* id128, int rank, int nRanks)
+{
+    if (!ctx || !id128 || nRanks < 1 || rank < 0 || rank >= nRanks) return ctx ? fail(ctx, UVRT_ERR_INVALID, "comm_init: bad arguments") : UVRT_ERR_INVALID;
+    if (!nccl_load()) return fail(ctx, UVRT_ERR_NCCL, "NCCL unavailable: %s", g_nccl.why.c_str());
+    Bind b(ctx);
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    if (ctx->comm) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    int r = g_nccl.CommInitRank(&ctx->comm, nRanks, id, rank);
+    if (r != kNcclSuccess) return fail(ctx, UVRT_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    ctx->rank = rank;
+    ctx->nRanks = nRanks;
+    return UVRT_OK;
+}
+
+int uvrt_reduce(uvrt_ctx* ctx)
+{
+    NEED_SCENE();
+    if (ctx->nRanks == 1 && !ctx->comm) return UVRT_OK;
+    if (!ctx->comm) return fail(ctx, UVRT_ERR_NCCL, "reduce: uvrt_comm_init was not called");
+    int r = g_nccl.GroupStart();
+    if (r == kNcclSuccess) r = g_nccl.AllReduce(ctx->dSum, ctx->dSum, (size_t)ctx->nTris, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+    if (r == kNcclSuccess) r = g_nccl.AllReduce(ctx->dMax, ctx->dMax, (size_t)ctx->nTris, kNcclFloat64, kNcclMax, ctx->comm, ctx->stream);
+    int r2 = g_nccl.GroupEnd();
+    if (r == kNcclSuccess) r = r2;
+    if (r != kNcclSuccess) return fail(ctx, UVRT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+    return UVRT_OK;
+}
+
+int uvrt_reduce_counts(uvrt_ctx* ctx)
+{
+    NEED_SCENE();
+    if (ctx->nRanks == 1 && !ctx->comm) return UVRT_OK;
+    if (!ctx->comm) return fail(ctx, UVRT_ERR_NCCL, "reduce_counts: uvrt_comm_init was not called");
+    int r = g_nccl.AllReduce(ctx->dCounts, ctx->dCounts, (size_t)ctx->nTris, kNcclInt32, kNcclSum, ctx->comm, ctx->stream);
+    if (r != kNcclSuccess) return fail(ctx, UVRT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+    return UVRT_OK;
+}
+
+// ---- options / measurement ---------------------------------------------------------------------------
+int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
+{
+    if (!ctx || !key) return UVRT_ERR_INVALID;
+    if (!strcmp(key, "extend_variant")) ctx->extendVariant = value;
+    else if (!strcmp(key, "stage_timing")) ctx->stageTiming = value;
+    else if (!strcmp(key, "hist_mode")) ctx->histMode = value;
+    else if (!strcmp(key, "blocks_per_sm")) ctx->blocksPerSm = value;
+    else return fail(ctx, UVRT_ERR_INVALID, "unknown option '%s'", key);
+    return UVRT_OK;
+}
+
+int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value)
+{
+    if (!ctx || !key || !value) return UVRT_ERR_INVALID;
+    if (!strcmp(key, "extend_variant")) *value = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
+    else if (!strcmp(key, "stage_timing")) *value = ctx->stageTiming;
+    else if (!strcmp(key, "hist_mode")) *value = ctx->histMode;
+    else if (!strcmp(key, "blocks_per_sm")) *value = ctx->blocksPerSm;
+    else if (!strcmp(key, "scene_tame")) *value = ctx->sceneTame;
+    else return fail(ctx, UVRT_ERR_INVALID, "unknown option '%s'", key);
+    return UVRT_OK;
+}
+
+int uvrt_stage_time(uvrt_ctx* ctx, uvrt_stage stage, double* ms, int64_t* launches)
+{
+    if (!ctx) return UVRT_ERR_INVALID;
+    Bind b(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    double sum = 0;
+    int64_t n = 0;
+    for (auto& t : ctx->timed) {
+        if (t.stage != (int)stage) continue;
+        float f = 0;
+        CK(cudaEventElapsedTime(&f, t.start, t.stop));
+        sum += f;
+        n++;
+    }
+    if (ms) *ms = sum;
+    if (launches) *launches = n;
+    return UVRT_OK;
+}
+
+int uvrt_stage_time_reset(uvrt_ctx* ctx)
+{
+    if (!ctx) return UVRT_ERR_INVALID;
+    Bind b(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& t : ctx->timed) { ctx->freeEvents.push_back(t.start); ctx->freeEvents.push_back(t.stop); }
+    ctx->timed.clear();
+    return UVRT_OK;
+}
+
+int64_t uvrt_launch_count(const uvrt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int uvrt_mark(uvrt_ctx* ctx, int slot)
+{
+    if (!ctx || slot < 0 || slot >= 16) return UVRT_ERR_INVALID;
+    Bind b(ctx);
+    CK(cudaEventRecord(ctx->marks[slot], ctx->stream));
+    return UVRT_OK;
+}
+
+int uvrt_elapsed_ms(uvrt_ctx* ctx, int a, int b2, float* ms)
+{
+    if (!ctx || !ms || a < 0 || a >= 16 || b2 < 0 || b2 >= 16) return UVRT_ERR_INVALID;
+    Bind b(ctx);
+    CK(cudaEventSynchronize(ctx->marks[b2]));
+    CK(cudaEventElapsedTime(ms, ctx->marks[a], ctx->marks[b2]));
+    return UVRT_OK;
+}
+
+// Diagnostic: on-device check of the shared-reciprocal division against __fdiv_rn.
+// out3 = {samples, one-step mismatches, two-step mismatches}.
+int uvrt_selftest_division(uvrt_ctx* ctx, int blocks, int itersPerThread, unsigned long long* out3)
+{
+    if (!ctx || !out3 || blocks <= 0 || itersPerThread <= 0) return UVRT_ERR_INVALID;
+    Bind b(ctx);
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc((void**)&d, 24));
+    CK(cudaMemsetAsync(d, 0, 24, ctx->stream));
+    k_selftest_division<<<blocks, 256, 0, ctx->stream>>>(d, itersPerThread, 0x9e3779b9u);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out3, d, 24, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, UVRT_ERR_CUDA, "selftest_division: %s", cudaGetErrorString(e));
+    return UVRT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,545 @@
+// uvrt_kernels.cuh -- sm_100a kernels of the wavefront hot path.
+//
+// Arithmetic contract (DESIGN.md "Parity"): every floating-point operation that the
+// reference's kernels perform is executed here as the same IEEE-754 operation, in the same
+// order, with round-to-nearest-even and WITHOUT fused multiply-adds.  That is what the
+// explicit __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn/__d*_rn intrinsics below are for: nvcc never
+// contracts them.  Where an FMA appears (the shared-reciprocal division) it computes a value
+// that is proven equal to the IEEE quotient.
+//
+// Reference being restated: /root/reference/cl/{tools,generate,extend,accumulate,shade,reset}.cl
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace uvrt {
+
+constexpr uint32_t kLeafFlag = 0x80000000u;   // child reference: leaf (low bits = first triangle slot)
+constexpr uint32_t kLastFlag = 0x80000000u;   // triangle slot: last triangle of its leaf
+constexpr float kNoHit = 1e30f;
+
+// ---- strict helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
+// OpenCL C select forms (tools: SURVEY App. A)
+__device__ __forceinline__ float clmin(float x, float y) { return y < x ? y : x; }
+__device__ __forceinline__ float clmax(float x, float y) { return x < y ? y : x; }
+
+// ---- RNG: tools.cl:2-4 ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t wang_hash(uint32_t s)
+{
+    s = (s ^ 61u) ^ (s >> 16);
+    s *= 9u;
+    s = s ^ (s >> 4);
+    s *= 0x27d4eb2du;
+    s = s ^ (s >> 15);
+    return s;
+}
+__device__ __forceinline__ uint32_t random_int(uint32_t& s)
+{
+    s ^= s << 13;
+    s ^= s >> 17;
+    s ^= s << 5;
+    return s;
+}
+__device__ __forceinline__ float random_float(uint32_t& s)
+{
+    return fm(__uint2float_rn(random_int(s)), 2.3283064365387e-10f);
+}
+
+struct RayRec {          // tools.cl:8-14, as two 16-byte halves
+    float4 a;            // dir.x dir.y dir.z orig.x
+    float4 b;            // orig.y orig.z dist triID(bits)
+};
+
+// generate.cl:8-40 for one work-item; returns the work-item's final RNG state
+__device__ __forceinline__ uint32_t generate_ray(int gid, float lx, float ly, float lz, float lightLength,
+                                                 uint32_t seedIn, RayRec& out)
+{
+    // generate.cl:13: the sum is evaluated in fp32 after the first (int) term; the final
+    // float -> uint conversion saturates (cvt.rzi.u32.f32), SURVEY App. B-2
+    float e = __int2float_rn((int)((uint32_t)gid * 17u + 1u));
+    e = fa(e, fm(lx, 13.0f));
+    e = fa(e, fm(ly, 7.0f));
+    e = fa(e, fm(lz, 11.0f));
+    e = fa(e, __uint2float_rn(seedIn >> 15));
+    uint32_t seed = wang_hash(__float2uint_rz(e));
+
+    float oy = fa(ly, fm(random_float(seed), lightLength));                 // generate.cl:16
+    float diry = fs(fm(random_float(seed), 2.0f), 1.0f);                    // generate.cl:22
+    double dy = (double)diry;
+    double len = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(dy, dy)));             // generate.cl:23
+    double x, z, d2;
+    do {                                                                    // generate.cl:25-28
+        float fx = fs(fm(random_float(seed), 2.0f), 1.0f);                  // x is drawn first
+        float fz = fs(fm(random_float(seed), 2.0f), 1.0f);
+        x = (double)fx;
+        z = (double)fz;
+        d2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(z, z));
+    } while (d2 > 1.0);
+    double scale = __ddiv_rn(len, __dsqrt_rn(d2));                          // generate.cl:29
+    out.a = make_float4(__double2float_rn(__dmul_rn(x, scale)), diry,
+                        __double2float_rn(__dmul_rn(z, scale)), lx);
+    out.b = make_float4(oy, lz, kNoHit, __uint_as_float(0u));
+    return seed;
+}
+
+__global__ void __launch_bounds__(256) k_generate(float4* __restrict__ rays, long long firstRay, long long nRays,
+                                                  float lx, float ly, float lz, float lightLength, uint32_t seedIn)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nRays) return;
+    RayRec r;
+    generate_ray((int)(firstRay + i), lx, ly, lz, lightLength, seedIn, r);
+    rays[2 * i] = r.a;
+    rays[2 * i + 1] = r.b;
+}
+
+// SEED chain (generate.cl:39): one thread replays work-item 0 of consecutive launches
+__global__ void k_seed_chain(const float* __restrict__ lightPos3, int nLaunches, float lightLength,
+                             uint32_t seedIn, uint32_t* __restrict__ seedsOut)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t seed = seedIn;
+    seedsOut[0] = seed;
+    for (int i = 0; i < nLaunches; i++) {
+        RayRec r;
+        seed = generate_ray(0, lightPos3[3 * i], lightPos3[3 * i + 1], lightPos3[3 * i + 2], lightLength, seed, r);
+        seedsOut[i + 1] = seed;
+    }
+}
+
+// ---- extend ---------------------------------------------------------------------------------
+// Division modes for the slab test (extend.cl:31-36 divides six times per box).
+//   DIV_IEEE      : __fdiv_rn, the literal restatement.
+//   DIV_MARKSTEIN2: r = RN(1/d) once per ray and axis, then q0 = n*r, two FMA residual
+//                   corrections; the result equals RN(n/d) (Markstein 1990: with a correctly
+//                   rounded reciprocal and a faithful q, one correction step rounds correctly;
+//                   the first step makes q faithful).  Only used for rays whose direction and
+//                   origin components keep every intermediate in the normal range, everything
+//                   else takes DIV_IEEE (see ray_is_tame()).
+//   DIV_MARKSTEIN1: one correction step; equal to RN(n/d) on every input tried (2e9 random and
+//                   adversarial pairs on the CPU, the on-device self-test) but without a proof.
+enum DivMode { DIV_IEEE = 0, DIV_MARKSTEIN2 = 2, DIV_MARKSTEIN1 = 1 };
+
+struct RayCtx {
+    float ox, oy, oz, dx, dy, dz;
+    float rx, ry, rz;     // RN(1/d) (Markstein modes)
+    float dist;
+    uint32_t tri;
+};
+
+template <int DIV>
+__device__ __forceinline__ float slab_q(float n, float d, float r)
+{
+    if (DIV == DIV_IEEE) {
+        return __fdiv_rn(n, d);
+    } else {
+        float q = fm(n, r);
+        float rem = __fmaf_rn(-d, q, n);
+        q = __fmaf_rn(rem, r, q);
+        if (DIV == DIV_MARKSTEIN2) {
+            rem = __fmaf_rn(-d, q, n);
+            q = __fmaf_rn(rem, r, q);
+        }
+        return q;
+    }
+}
+
+// extend.cl:29-38.  bmin/bmax carry the box in .xyz
+template <int DIV>
+__device__ __forceinline__ float intersect_aabb(const RayCtx& ray, const float4& bmin, const float4& bmax)
+{
+    float tx1 = slab_q<DIV>(fs(bmin.x, ray.ox), ray.dx, ray.rx), tx2 = slab_q<DIV>(fs(bmax.x, ray.ox), ray.dx, ray.rx);
+    float ty1 = slab_q<DIV>(fs(bmin.y, ray.oy), ray.dy, ray.ry), ty2 = slab_q<DIV>(fs(bmax.y, ray.oy), ray.dy, ray.ry);
+    float tz1 = slab_q<DIV>(fs(bmin.z, ray.oz), ray.dz, ray.rz), tz2 = slab_q<DIV>(fs(bmax.z, ray.oz), ray.dz, ray.rz);
+    float tmin, tmax;
+    if (DIV == DIV_IEEE) {
+        // NaNs are possible here (0/0): keep OpenCL's select forms exactly
+        tmin = clmin(tx1, tx2); tmax = clmax(tx1, tx2);
+        tmin = clmax(tmin, clmin(ty1, ty2)); tmax = clmin(tmax, clmax(ty1, ty2));
+        tmin = clmax(tmin, clmin(tz1, tz2)); tmax = clmin(tmax, clmax(tz1, tz2));
+    } else {
+        // tame rays produce no NaN; fminf/fmaxf then agree with the select forms up to the
+        // sign of a zero, which no comparison below can observe
+        tmin = fminf(tx1, tx2); tmax = fmaxf(tx1, tx2);
+        tmin = fmaxf(tmin, fminf(ty1, ty2)); tmax = fminf(tmax, fmaxf(ty1, ty2));
+        tmin = fmaxf(tmin, fminf(tz1, tz2)); tmax = fminf(tmax, fmaxf(tz1, tz2));
+    }
+    return (tmax >= tmin && tmin < ray.dist && tmax > 0.0f) ? tmin : kNoHit;
+}
+
+// extend.cl:6-27 with edge1 = v1-v0 and edge2 = v2-v0 formed at upload time (the same IEEE
+// subtractions, done once instead of once per test).  t0.w = triID | last-in-leaf flag.
+__device__ __forceinline__ void intersect_tri(RayCtx& ray, const float4& t0, const float4& e1, const float4& e2)
+{
+    float hx = fs(fm(ray.dy, e2.z), fm(ray.dz, e2.y));
+    float hy = fs(fm(ray.dz, e2.x), fm(ray.dx, e2.z));
+    float hz = fs(fm(ray.dx, e2.y), fm(ray.dy, e2.x));
+    float a = fa(fa(fm(e1.x, hx), fm(e1.y, hy)), fm(e1.z, hz));
+    if (fabsf(a) < 0.00001f) return;
+    float f = __fdiv_rn(1.0f, a);
+    float sx = fs(ray.ox, t0.x), sy = fs(ray.oy, t0.y), sz = fs(ray.oz, t0.z);
+    float u = fm(f, fa(fa(fm(sx, hx), fm(sy, hy)), fm(sz, hz)));
+    if ((u < 0.0f) | (u > 1.0f)) return;
+    float qx = fs(fm(sy, e1.z), fm(sz, e1.y));
+    float qy = fs(fm(sz, e1.x), fm(sx, e1.z));
+    float qz = fs(fm(sx, e1.y), fm(sy, e1.x));
+    float v = fm(f, fa(fa(fm(ray.dx, qx), fm(ray.dy, qy)), fm(ray.dz, qz)));
+    if ((v < 0.0f) | (fa(u, v) > 1.0f)) return;
+    float t = fm(f, fa(fa(fm(e2.x, qx), fm(e2.y, qy)), fm(e2.z, qz)));
+    if (t > 0.0001f && t < ray.dist) {
+        ray.dist = t;
+        ray.tri = __float_as_uint(t0.w) & ~kLastFlag;
+    }
+}
+
+// A ray is "tame" when the Markstein quotient provably equals the IEEE one for every box of a
+// scene whose coordinates are 0 or >= 2^-20 in magnitude (checked at upload): direction
+// components in [2^-30, 2], origin components 0 or >= 2^-20.  Then n = a - o is 0 or >= 2^-43,
+// |q| <= 2^36, and the residual fma(-d, q, n) is exact and far from the denormal range.
+__device__ __forceinline__ bool ray_is_tame(const RayCtx& r)
+{
+    const float dlo = 9.31322574615478515625e-10f;  // 2^-30
+    const float olo = 9.5367431640625e-07f;         // 2^-20
+    float ax = fabsf(r.dx), ay = fabsf(r.dy), az = fabsf(r.dz);
+    bool d_ok = ax >= dlo && ay >= dlo && az >= dlo && ax <= 2.0f && ay <= 2.0f && az <= 2.0f;
+    float px = fabsf(r.ox), py = fabsf(r.oy), pz = fabsf(r.oz);
+    bool o_ok = (px == 0.0f || (px >= olo && px <= 1048576.0f)) && (py == 0.0f || (py >= olo && py <= 1048576.0f)) &&
+                (pz == 0.0f || (pz >= olo && pz <= 1048576.0f));
+    return d_ok && o_ok;
+}
+
+// extend.cl:40-81.  The traversal order, the tie rules (dist1 > dist2 swaps, so ties keep child
+// 1 first; strict t < dist keeps the first-found triangle) and the distance culling are the
+// reference's.  `pairs` holds, per inner node, its two children's boxes and references
+// (4 x float4); `wtris` holds leaf triangles in leaf order (3 x float4).
+template <int DIV, int STACK>
+__device__ __forceinline__ void bvh_intersect(RayCtx& ray, const float4* __restrict__ pairs,
+                                              const float4* __restrict__ wtris, uint32_t rootRef)
+{
+    uint32_t stack[STACK];
+    int sp = 0;
+    uint32_t cur = rootRef;
+    for (;;) {
+        if (cur & kLeafFlag) {
+            uint32_t slot = cur & ~kLeafFlag;
+            uint32_t w;
+            do {
+                const float4* t = wtris + 3ull * slot;
+                float4 t0 = __ldg(t), e1 = __ldg(t + 1), e2 = __ldg(t + 2);
+                w = __float_as_uint(t0.w);
+                intersect_tri(ray, t0, e1, e2);
+                slot++;
+            } while (!(w & kLastFlag));
+            if (sp == 0) break;
+            cur = stack[--sp];
+            continue;
+        }
+        const float4* p = pairs + 4ull * cur;
+        float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+        float d1 = intersect_aabb<DIV>(ray, q0, q1);
+        float d2 = intersect_aabb<DIV>(ray, q2, q3);
+        uint32_t c1 = __float_as_uint(q0.w), c2 = __float_as_uint(q2.w);
+        if (d1 > d2) {
+            float d = d1; d1 = d2; d2 = d;
+            uint32_t c = c1; c1 = c2; c2 = c;
+        }
+        if (d1 == kNoHit) {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        } else {
+            cur = c1;
+            if (d2 != kNoHit) stack[sp++] = c2;
+        }
+    }
+}
+
+template <int DIV, int STACK>
+__device__ __forceinline__ void trace_one(RayCtx& ray, const float4* __restrict__ pairs,
+                                          const float4* __restrict__ wtris, uint32_t rootRef, bool sceneTame)
+{
+    if (DIV == DIV_IEEE) {
+        bvh_intersect<DIV_IEEE, STACK>(ray, pairs, wtris, rootRef);
+    } else {
+        if (sceneTame && ray_is_tame(ray)) {
+            ray.rx = __frcp_rn(ray.dx);
+            ray.ry = __frcp_rn(ray.dy);
+            ray.rz = __frcp_rn(ray.dz);
+            bvh_intersect<DIV, STACK>(ray, pairs, wtris, rootRef);
+        } else {
+            bvh_intersect<DIV_IEEE, STACK>(ray, pairs, wtris, rootRef);
+        }
+    }
+}
+
+__device__ __forceinline__ void load_ray(const float4* __restrict__ rays, long long i, RayCtx& ray)
+{
+    float4 a = rays[2 * i], b = rays[2 * i + 1];
+    ray.dx = a.x; ray.dy = a.y; ray.dz = a.z;
+    ray.ox = a.w; ray.oy = b.x; ray.oz = b.y;
+    ray.dist = b.z;
+    ray.tri = __float_as_uint(b.w);
+    ray.rx = ray.ry = ray.rz = 0.0f;
+}
+
+__device__ __forceinline__ void store_hit(float4* __restrict__ rays, long long i, const RayCtx& ray)
+{
+    // dist, triID occupy bytes 24..31 of the 32-byte ray record
+    float2* p = reinterpret_cast<float2*>(rays + 2 * i + 1) + 1;
+    *p = make_float2(ray.dist, __uint_as_float(ray.tri));
+}
+
+// Variant A: one thread per ray, the literal control flow of extend.cl:85-99.
+template <int DIV, int STACK>
+__global__ void __launch_bounds__(128) k_extend_simple(int* __restrict__ counts, const float4* __restrict__ wtris,
+                                                       float4* __restrict__ rays, const float4* __restrict__ pairs,
+                                                       uint32_t rootRef, long long nRays, int sceneTame)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nRays) return;
+    RayCtx ray;
+    load_ray(rays, i, ray);
+    trace_one<DIV, STACK>(ray, pairs, wtris, rootRef, sceneTame != 0);
+    store_hit(rays, i, ray);
+    if (ray.dist != kNoHit) atomicAdd(&counts[ray.tri], 1);
+}
+
+// Variant B: persistent warps that pull rays from a global queue.  Lanes whose ray has finished
+// are refilled together (one warp-aggregated atomicAdd on the queue head per refill) once fewer
+// than REFILL lanes are still busy, so a warp is not held hostage by its longest ray.  Inside,
+// every lane alternates between at most K inner-node steps and one leaf visit; the per-ray
+// sequence of box tests, triangle tests and distance updates is exactly variant A's.
+// HIST = 1 counts hits in a shared-memory table first (block-level pre-reduction of hot triangle
+// IDs) and only spills colliding IDs and the final table to the global counters.
+template <int HBITS>
+struct HitTable {
+    uint32_t tag[1 << HBITS];
+    int cnt[1 << HBITS];
+};
+
+template <int HBITS>
+__device__ __forceinline__ void hist_add(HitTable<HBITS>* tab, int* __restrict__ counts, uint32_t tri)
+{
+    uint32_t slot = (tri * 2654435761u) >> (32 - HBITS);
+    uint32_t old = atomicCAS(&tab->tag[slot], 0xffffffffu, tri);
+    if (old == 0xffffffffu || old == tri) atomicAdd(&tab->cnt[slot], 1);
+    else atomicAdd(&counts[tri], 1);
+}
+
+template <int DIV, int STACK, int K, int REFILL, int HIST, int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS)
+k_extend_persist(int* __restrict__ counts, const float4* __restrict__ wtris, float4* __restrict__ rays,
+                 const float4* __restrict__ pairs, uint32_t rootRef, uint32_t nRays, int sceneTame,
+                 unsigned int* __restrict__ queueHead)
+{
+    constexpr int HBITS = 11;
+    __shared__ HitTable<HIST ? HBITS : 1> tab;
+    if (HIST) {
+        for (int i = threadIdx.x; i < (1 << HBITS); i += THREADS) { tab.tag[i] = 0xffffffffu; tab.cnt[i] = 0; }
+        __syncthreads();
+    }
+    uint32_t stack[STACK];
+    const unsigned lane = threadIdx.x & 31u;
+    RayCtx ray;
+    ray.ox = ray.oy = ray.oz = ray.dx = ray.dy = ray.dz = ray.rx = ray.ry = ray.rz = 0.0f;
+    ray.dist = kNoHit; ray.tri = 0;
+    uint32_t cur = 0, rayIdx = 0xffffffffu;
+    int sp = 0;
+    bool busy = false, tame = false, drained = false;
+
+    for (;;) {
+        // ---- refill (warp-converged) ----
+        unsigned idle = __ballot_sync(0xffffffffu, !busy);
+        if (idle && !drained) {
+            int leader = __ffs(idle) - 1;
+            unsigned cnt = __popc(idle);
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(queueHead, cnt);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!busy) {
+                unsigned idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (base < nRays && idx < nRays) {
+                    rayIdx = idx;
+                    load_ray(rays, idx, ray);
+                    tame = false;
+                    if (DIV != DIV_IEEE && sceneTame && ray_is_tame(ray)) {
+                        tame = true;
+                        ray.rx = __frcp_rn(ray.dx); ray.ry = __frcp_rn(ray.dy); ray.rz = __frcp_rn(ray.dz);
+                    }
+                    cur = rootRef; sp = 0; busy = true;
+                }
+            }
+            // base is warp-uniform: once the queue is past the end nobody asks again
+            if (base >= nRays || nRays - base < cnt) drained = true;
+        }
+        unsigned act = __ballot_sync(0xffffffffu, busy);
+        if (act == 0u) break;
+
+        // ---- traverse until too few lanes are busy ----
+        for (;;) {
+#pragma unroll 1
+            for (int k = 0; k < K && busy && !(cur & kLeafFlag); k++) {
+                const float4* p = pairs + 4ull * cur;
+                float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+                float d1, d2;
+                if (DIV == DIV_IEEE || !tame) {
+                    d1 = intersect_aabb<DIV_IEEE>(ray, q0, q1);
+                    d2 = intersect_aabb<DIV_IEEE>(ray, q2, q3);
+                } else {
+                    d1 = intersect_aabb<DIV>(ray, q0, q1);
+                    d2 = intersect_aabb<DIV>(ray, q2, q3);
+                }
+                uint32_t c1 = __float_as_uint(q0.w), c2 = __float_as_uint(q2.w);
+                if (d1 > d2) {
+                    float d = d1; d1 = d2; d2 = d;
+                    uint32_t c = c1; c1 = c2; c2 = c;
+                }
+                if (d1 == kNoHit) {
+                    if (sp == 0) busy = false; else cur = stack[--sp];
+                } else {
+                    cur = c1;
+                    if (d2 != kNoHit) stack[sp++] = c2;
+                }
+            }
+            if (busy && (cur & kLeafFlag)) {
+                uint32_t slot = cur & ~kLeafFlag;
+                uint32_t w;
+                do {
+                    const float4* t = wtris + 3ull * slot;
+                    float4 t0 = __ldg(t), e1 = __ldg(t + 1), e2 = __ldg(t + 2);
+                    w = __float_as_uint(t0.w);
+                    intersect_tri(ray, t0, e1, e2);
+                    slot++;
+                } while (!(w & kLastFlag));
+                if (sp == 0) busy = false; else cur = stack[--sp];
+            }
+            if (!busy && rayIdx != 0xffffffffu) {
+                // the ray just finished: write back (extend.cl:26 writes in place) and count
+                store_hit(rays, rayIdx, ray);
+                if (ray.dist != kNoHit) {
+                    if (HIST) hist_add<HBITS>(reinterpret_cast<HitTable<HBITS>*>(&tab), counts, ray.tri);
+                    else atomicAdd(&counts[ray.tri], 1);
+                }
+                rayIdx = 0xffffffffu;
+            }
+            act = __ballot_sync(0xffffffffu, busy);
+            if (act == 0u) break;
+            if (!drained && __popc(act) < REFILL) break;
+        }
+    }
+    if (HIST) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < (1 << HBITS); i += THREADS) {
+            int c = tab.cnt[i];
+            if (c) atomicAdd(&counts[tab.tag[i]], c);
+        }
+    }
+}
+
+// ---- per-triangle passes ------------------------------------------------------------------
+// accumulate.cl:4-14
+__global__ void __launch_bounds__(256) k_accumulate(double* __restrict__ photonMap, double* __restrict__ maxPhotonMap,
+                                                    int* __restrict__ temp, float timeStep, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double c = (double)temp[i];
+    photonMap[i] = __dadd_rn(photonMap[i], __dmul_rn(c, (double)timeStep));
+    double m = maxPhotonMap[i];
+    maxPhotonMap[i] = m < c ? c : m;
+    temp[i] = 0;
+}
+
+// shade.cl:23-41; `verts` is the reference-layout triangle array (64 B per triangle)
+__global__ void __launch_bounds__(256) k_compute_dosage(const double* __restrict__ photonMap, float* __restrict__ dosage,
+                                                        const float4* __restrict__ verts, int photonsPerLight,
+                                                        float scaledPower, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v0 = __ldg(verts + 4ull * i), v1 = __ldg(verts + 4ull * i + 1), v2 = __ldg(verts + 4ull * i + 2);
+    float ax = fs(v0.x, v1.x), ay = fs(v0.y, v1.y), az = fs(v0.z, v1.z);
+    float bx = fs(v0.x, v2.x), by = fs(v0.y, v2.y), bz = fs(v0.z, v2.z);
+    float cx = fs(fm(ay, bz), fm(az, by));
+    float cy = fs(fm(az, bx), fm(ax, bz));
+    float cz = fs(fm(ax, by), fm(ay, bx));
+    float area = __fdiv_rn(__fsqrt_rn(fa(fa(fm(cx, cx), fm(cy, cy)), fm(cz, cz))), 2.0f);
+    double num = __dmul_rn((double)scaledPower, photonMap[i]);
+    float den = fm(area, __int2float_rn(photonsPerLight));
+    dosage[i] = __double2float_rn(__ddiv_rn(num, (double)den));
+}
+
+// shade.cl:4-21
+__device__ __forceinline__ void heatmap(float v, float& r, float& g, float& b)
+{
+    const float mid = 0.5f, hi = 0.75f, lo = 0.25f;
+    if (v > mid) {
+        if (v > hi) { r = 1.0f; g = __fdiv_rn(fs(1.0f, v), fs(1.0f, hi)); b = 0.0f; }
+        else        { r = __fdiv_rn(fs(v, mid), fs(hi, mid)); g = 1.0f; b = 0.0f; }
+    } else {
+        if (v > lo) { r = 0.0f; g = 1.0f; b = __fdiv_rn(fs(mid, v), fs(mid, lo)); }
+        else        { r = 0.0f; g = __fdiv_rn(v, lo); b = 1.0f; }
+    }
+}
+
+// shade.cl:43-71: nine floats per triangle (the same colour on its three vertices)
+__global__ void __launch_bounds__(256) k_dosage_to_color(const float* __restrict__ dosage, float* __restrict__ color,
+                                                         float minValue, int thresholdView, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float maxValue = fm(minValue, 2.0f);
+    float norm = __fdiv_rn(dosage[i], maxValue);
+    float r, g, b;
+    if (thresholdView && norm < 0.5f) { r = 0.0f; g = 0.0f; b = fm(norm, 2.0f); }
+    else heatmap(norm, r, g, b);
+    float* c = color + 9ull * i;
+    c[0] = r; c[1] = g; c[2] = b;
+    c[3] = r; c[4] = g; c[5] = b;
+    c[6] = r; c[7] = g; c[8] = b;
+}
+
+// reset.cl:4-26
+__global__ void __launch_bounds__(256) k_reset(double* __restrict__ photonMap, double* __restrict__ maxPhotonMap,
+                                               int* __restrict__ temp, float* __restrict__ color, int resetColor, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    photonMap[i] = 0.0;
+    maxPhotonMap[i] = 0.0;
+    temp[i] = 0;
+    if (!resetColor) return;
+    float* c = color + 9ull * i;
+#pragma unroll
+    for (int k = 0; k < 9; k++) c[k] = 0.0f;
+}
+
+// ---- on-device self-test of the shared-reciprocal division -----------------------------------
+// Draws (a, o, d) with the magnitudes ray_is_tame() admits and counts quotients that differ from
+// __fdiv_rn.  out[0] = samples, out[1] = mismatches of one-step, out[2] = mismatches of two-step.
+__global__ void __launch_bounds__(256) k_selftest_division(unsigned long long* __restrict__ out, int iters, uint32_t salt)
+{
+    uint32_t s = wang_hash((blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + salt) | 1u;
+    unsigned long long bad1 = 0, bad2 = 0;
+    for (int it = 0; it < iters; it++) {
+        uint32_t md = random_int(s) & 0x7fffffu, mn = random_int(s) & 0x7fffffu, e = random_int(s);
+        int ed = -(int)(e % 31u), en = -43 + (int)((e >> 8) % 49u);
+        if ((e >> 20) & 1u) md = ((e >> 21) & 1u) ? 0x7fffffu - (md & 0xffu) : (md & 0xffu);
+        if ((e >> 22) & 1u) mn = ((e >> 23) & 1u) ? 0x7fffffu - (mn & 0xffu) : (mn & 0xffu);
+        float d = __uint_as_float(((uint32_t)(ed + 127) << 23) | md | (((e >> 30) & 1u) << 31));
+        float n = __uint_as_float(((uint32_t)(en + 127) << 23) | mn | ((e >> 31) << 31));
+        float r = __frcp_rn(d);
+        float q = __fdiv_rn(n, d);
+        float q1 = slab_q<DIV_MARKSTEIN1>(n, d, r);
+        float q2 = slab_q<DIV_MARKSTEIN2>(n, d, r);
+        bad1 += (__float_as_uint(q1) != __float_as_uint(q));
+        bad2 += (__float_as_uint(q2) != __float_as_uint(q));
+    }
+    atomicAdd(&out[0], (unsigned long long)iters);
+    atomicAdd(&out[1], bad1);
+    atomicAdd(&out[2], bad2);
+}
+
+} // namespace uvrt

@@ -1,0 +1,223 @@
+// mesh.cpp -- binary glTF (.glb) room loader and floor-height estimate.
+// Behaviour follows /root/reference/mesh.cpp:5-136: only meshes[0].primitives[0] is read,
+// POSITION (float VEC3) is de-indexed through u16 or u32 indices into 64-byte Tri records,
+// then the floor height is estimated and the BVH built.  The container is parsed directly
+// (12-byte header, JSON chunk, BIN chunk) instead of through tinygltf.
+#include "precomp.h"
+#include "json_min.h"
+#include <fstream>
+
+namespace Tmpl8 {
+
+static std::string g_assetRoot;
+static bool g_assetRootInit = false;
+
+const std::string& AssetRoot()
+{
+    if (!g_assetRootInit) {
+        const char* e = getenv("UVRT_ASSET_ROOT");
+        if (e && *e) {
+            g_assetRoot = e;
+            if (g_assetRoot.back() != '/') g_assetRoot += '/';
+        }
+        g_assetRootInit = true;
+    }
+    return g_assetRoot;
+}
+
+void SetAssetRoot(const std::string& dir)
+{
+    g_assetRoot = dir;
+    if (!g_assetRoot.empty() && g_assetRoot.back() != '/') g_assetRoot += '/';
+    g_assetRootInit = true;
+}
+
+Mesh::~Mesh() { Release(); }
+
+void Mesh::Release()
+{
+    delete bvh; bvh = 0;
+    free(triangles); triangles = 0;
+    delete[] vertices; vertices = 0;
+    delete[] uvcoords; uvcoords = 0;
+    triangleCount = 0;
+    vertexCount = 0;
+    loadedMesh = false;
+}
+
+namespace {
+
+uint32_t rd32(const std::vector<char>& b, size_t off)
+{
+    uint32_t v;
+    memcpy(&v, &b[off], 4);
+    return v;
+}
+
+struct AccessorView {
+    const unsigned char* data = nullptr;
+    size_t count = 0, stride = 0;
+    int componentType = 0;
+};
+
+// resolves accessor -> bufferView -> the GLB's BIN chunk
+bool resolve(const uvrt_json::Value& js, const unsigned char* bin, size_t binLen, long long accessorIdx,
+             size_t elemBytes, AccessorView& out, std::string& err)
+{
+    const uvrt_json::Value& acc = js["accessors"][(size_t)accessorIdx];
+    if (accessorIdx < 0 || acc.kind != uvrt_json::Value::Object) { err = "accessor missing"; return false; }
+    const uvrt_json::Value& bv = js["bufferViews"][(size_t)acc["bufferView"].as_int(-1)];
+    if (bv.kind != uvrt_json::Value::Object) { err = "bufferView missing"; return false; }
+    if (bv["buffer"].as_int(0) != 0) { err = "only the embedded GLB buffer is supported"; return false; }
+    size_t off = (size_t)bv["byteOffset"].as_int(0) + (size_t)acc["byteOffset"].as_int(0);
+    out.count = (size_t)acc["count"].as_int(0);
+    out.componentType = (int)acc["componentType"].as_int(0);
+    out.stride = (size_t)bv["byteStride"].as_int(0);
+    if (out.stride == 0) out.stride = elemBytes;
+    if (out.count && off + (out.count - 1) * out.stride + elemBytes > binLen) { err = "accessor exceeds the BIN chunk"; return false; }
+    out.data = bin + off;
+    return true;
+}
+
+} // namespace
+
+void Mesh::LoadMesh()
+{
+    std::cout << "Loading mesh " << std::endl;
+    Release();
+    lastError.clear();
+    std::string path = AssetRoot() + "rooms/" + modelFile + ".glb";
+    std::ifstream f(path, std::ios::binary);
+    if (!f) { lastError = "cannot open " + path; printf("Failed to parse glTF: %s\n", lastError.c_str()); return; }
+    std::vector<char> file((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    auto bail = [&](const std::string& why) { lastError = path + ": " + why; printf("Failed to parse glTF: %s\n", lastError.c_str()); };
+    if (file.size() < 20 || memcmp(file.data(), "glTF", 4) != 0) return bail("not a binary glTF file");
+    if (rd32(file, 4) != 2) return bail("unsupported glTF container version");
+    size_t total = std::min<size_t>(rd32(file, 8), file.size());
+    size_t jsonLen = rd32(file, 12);
+    if (rd32(file, 16) != 0x4E4F534Au || 20 + jsonLen > total) return bail("missing JSON chunk");
+    uvrt_json::Value js;
+    std::string jerr;
+    if (!uvrt_json::Parser(&file[20], jsonLen).parse(js, jerr)) return bail("JSON: " + jerr);
+    size_t binHdr = 20 + jsonLen;
+    if (binHdr + 8 > total || rd32(file, binHdr + 4) != 0x004E4942u) return bail("missing BIN chunk");
+    size_t binLen = rd32(file, binHdr);
+    if (binHdr + 8 + binLen > total) return bail("truncated BIN chunk");
+    const unsigned char* bin = (const unsigned char*)&file[binHdr + 8];
+
+    const uvrt_json::Value& prim = js["meshes"][0]["primitives"][0];
+    if (prim.kind != uvrt_json::Value::Object) return bail("meshes[0].primitives[0] missing");
+    if (!prim["attributes"]["POSITION"].is_number() || !prim["indices"].is_number()) return bail("primitive needs POSITION and indices");
+    AccessorView pos, idx, uv;
+    std::string err;
+    if (!resolve(js, bin, binLen, prim["attributes"]["POSITION"].as_int(), 12, pos, err)) return bail("POSITION: " + err);
+    if (pos.componentType != 5126) return bail("POSITION must be float");
+    long long idxAcc = prim["indices"].as_int();
+    int idxType = (int)js["accessors"][(size_t)idxAcc]["componentType"].as_int(0);
+    if (idxType != 5123 && idxType != 5125) return bail("indices must be u16 or u32");   // mesh.cpp:44-51
+    size_t idxBytes = idxType == 5123 ? 2 : 4;
+    if (!resolve(js, bin, binLen, idxAcc, idxBytes, idx, err)) return bail("indices: " + err);
+    bool haveUv = prim["attributes"]["TEXCOORD_0"].is_number() &&
+                  resolve(js, bin, binLen, prim["attributes"]["TEXCOORD_0"].as_int(), 8, uv, err) && uv.componentType == 5126;
+
+    const size_t nTri = idx.count / 3;
+    if (nTri == 0) return bail("no triangles");
+    void* mem = nullptr;
+    if (posix_memalign(&mem, 64, sizeof(Tri) * nTri) != 0) return bail("out of memory");
+    memset(mem, 0, sizeof(Tri) * nTri);   // the reference leaves the pad lanes uninitialised
+    triangles = (Tri*)mem;
+    vertices = new float[nTri * 9];
+    uvcoords = new float[nTri * 6]();
+    auto index_at = [&](size_t k) -> size_t {
+        const unsigned char* p = idx.data + k * idx.stride;
+        if (idxBytes == 2) { uint16_t v; memcpy(&v, p, 2); return v; }
+        uint32_t v; memcpy(&v, p, 4); return v;
+    };
+    for (size_t t = 0; t < nTri; t++) {
+        float3_strict* dst[3] = {&triangles[t].vertex0, &triangles[t].vertex1, &triangles[t].vertex2};
+        for (int c = 0; c < 3; c++) {
+            size_t v = index_at(t * 3 + c);
+            if (v >= pos.count) { Release(); return bail("vertex index out of range"); }
+            float p[3];
+            memcpy(p, pos.data + v * pos.stride, 12);
+            *dst[c] = make_float3_strict(p[0], p[1], p[2]);
+            vertices[t * 9 + c * 3 + 0] = p[0];
+            vertices[t * 9 + c * 3 + 1] = p[1];
+            vertices[t * 9 + c * 3 + 2] = p[2];
+            if (haveUv && v < uv.count) memcpy(&uvcoords[t * 6 + c * 2], uv.data + v * uv.stride, 8);
+        }
+    }
+    vertexCount = (int)(nTri * 9);
+    triangleCount = (int)nTri;
+
+    DetermineFloorHeight();
+
+    std::cout << "Vertex count: " << vertexCount << " triangle count: " << triangleCount << std::endl;
+    bvh = new BVH(this);
+    std::cout << "BVH size: " << bvh->nodesUsed << std::endl;
+    BindMesh();
+    loadedMesh = true;
+}
+
+void Mesh::SetTriangles(const Tri* tris, int n, bool buildBvh)
+{
+    Release();
+    if (n <= 0) return;
+    void* mem = nullptr;
+    if (posix_memalign(&mem, 64, sizeof(Tri) * (size_t)n) != 0) return;
+    memcpy(mem, tris, sizeof(Tri) * (size_t)n);
+    triangles = (Tri*)mem;
+    triangleCount = n;
+    vertexCount = n * 9;
+    vertices = new float[(size_t)n * 9];
+    uvcoords = new float[(size_t)n * 6]();
+    for (int t = 0; t < n; t++) {
+        const float3_strict* src[3] = {&triangles[t].vertex0, &triangles[t].vertex1, &triangles[t].vertex2};
+        for (int c = 0; c < 3; c++) {
+            vertices[t * 9 + c * 3 + 0] = src[c]->x;
+            vertices[t * 9 + c * 3 + 1] = src[c]->y;
+            vertices[t * 9 + c * 3 + 2] = src[c]->z;
+        }
+    }
+    DetermineFloorHeight();
+    if (buildBvh) bvh = new BVH(this);
+    loadedMesh = true;
+}
+
+// Floor = centre of the fullest of 48 height bins between the lowest vertex (at most 0) and 0.
+// Same strict comparisons and fp32 bin edges as mesh.cpp:100-136 of the reference (whose
+// maxVal is never raised above 0: rooms entirely above y = 0 get floor 0).
+void Mesh::DetermineFloorHeight()
+{
+    const int binCount = 48;
+    const int nVerts = vertexCount / 3;
+    float maxVal = 0.0f, minVal = 0.0f;
+    for (int i = 0; i < nVerts; i++) {
+        float y = vertices[i * 3 + 1];
+        if (y < minVal) minVal = y;
+    }
+    const float range = maxVal - minVal;
+    float lo[binCount], hi[binCount];
+    for (int j = 0; j < binCount; j++) {
+        lo[j] = j * range / binCount + minVal;
+        hi[j] = (j + 1) * range / binCount + minVal;
+    }
+    int hist[binCount] = {0};
+    for (int i = 0; i < nVerts; i++) {
+        const float y = vertices[i * 3 + 1];
+        for (int j = 0; j < binCount; j++)
+            if (lo[j] < y && y < hi[j]) hist[j]++;
+    }
+    int maxCount = 0, maxIndex = -1;
+    for (int j = 0; j < binCount; j++)
+        if (hist[j] > maxCount) { maxIndex = j; maxCount = hist[j]; }
+    floorHeight = (maxIndex + 0.5f) * range / binCount + minVal;
+}
+
+void Mesh::BindMesh()
+{
+    // The reference creates the GL vertex / uv / colour buffers here (mesh.cpp:138-200).
+    // The colour buffer lives in libuvrt (UVRT_BUF_COLOR); there is nothing to bind.
+}
+
+} // namespace Tmpl8

@@ -1,0 +1,306 @@
+// raytracer.cpp -- RayTracer on the libuvrt C ABI.
+// Host sequencing follows /root/reference/raytracer.cpp:12-300: which stage runs when, the
+// scalar arguments each stage gets (photons per light, scaled power, dose divisor) and the
+// route-file schema.  The OpenCL plumbing (Kernel, Buffer, SetArgument) is replaced by uvrt_* calls.
+#include "precomp.h"
+#include "xml_min.h"
+#include "../../include/uvrt.h"
+#include <fstream>
+#include <sstream>
+
+namespace Tmpl8 {
+
+RayTracer::~RayTracer()
+{
+    if (ctx) uvrt_destroy(ctx);
+    delete[] dosageMap;
+}
+
+bool RayTracer::Check(int rc, const char* what)
+{
+    if (rc == UVRT_OK) return true;
+    ok = false;
+    lastError = std::string(what) + ": " + (ctx ? uvrt_last_error(ctx) : uvrt_last_error(nullptr));
+    std::cerr << "uvrt error " << rc << " in " << lastError << std::endl;
+    return false;
+}
+
+void RayTracer::AddLamp()
+{
+    LightPos initLightPos;
+    initLightPos.position = make_float2(0.0f, 0.0f);
+    initLightPos.duration = 1;
+    lightPositions.push_back(initLightPos);
+    UpdatePhotonsPerLight();
+}
+
+void RayTracer::UploadScene()
+{
+    if (!ctx || !mesh || !mesh->bvh) return;
+    Check(uvrt_upload_scene(ctx, mesh->triangles, mesh->triangleCount, mesh->bvh->bvhNode, (int)mesh->bvh->nodesUsed,
+                            mesh->bvh->triIdx),
+          "upload_scene");
+}
+
+void RayTracer::Init(Mesh* m)
+{
+    mesh = m;
+    LoadRoute(defaultRouteFile);
+    if (!ctx) {
+        if (!Check(uvrt_create(&ctx, device), "uvrt_create")) return;
+    }
+    seedState = 0;
+    launchCounter = 0;
+    seedQueue.clear();
+    seedQueueHead = 0;
+    if (!mesh || !mesh->loadedMesh || !mesh->bvh) {
+        ok = false;
+        lastError = "Init: mesh not loaded";
+        return;
+    }
+    UploadScene();
+}
+
+void RayTracer::UpdatePhotonsPerLight()
+{
+    // an even count, as in the reference (raytracer.cpp:63)
+    if (lightPositions.empty()) { photonsPerLight = 0; return; }
+    photonsPerLight = (photonCount / (int)lightPositions.size()) & ~1;
+}
+
+void RayTracer::ComputeDosageMap()
+{
+    if (!ok || lightPositions.empty()) return;
+    // SEED of every launch of the remaining passes in one device call, unless the queue built by
+    // an earlier pass still matches the route
+    const size_t L = lightPositions.size();
+    std::vector<float> pos(3 * L);
+    for (size_t i = 0; i < L; i++) {
+        pos[3 * i + 0] = lightPositions[i].position.x;
+        pos[3 * i + 1] = mesh->floorHeight + lightHeight;
+        pos[3 * i + 2] = lightPositions[i].position.y;
+    }
+    bool queued = seedQueue.size() - seedQueueHead >= L &&
+                  memcmp(&seedQueuePos[3 * seedQueueHead], pos.data(), sizeof(float) * 3 * L) == 0;
+    if (!queued) {
+        int passes = maxIterations - currIterations;
+        if (passes < 1) passes = 1;
+        std::vector<float> all(3 * L * (size_t)passes);
+        for (int p = 0; p < passes; p++) memcpy(&all[3 * L * p], pos.data(), sizeof(float) * 3 * L);
+        std::vector<uint32_t> seeds(L * (size_t)passes + 1);
+        if (!Check(uvrt_seed_chain(ctx, all.data(), (int)(L * passes), lightLength, seedState, seeds.data()), "seed_chain")) return;
+        seedQueue.assign(seeds.begin() + 1, seeds.end());
+        seedQueuePos.swap(all);
+        seedQueueHead = 0;
+    }
+    for (LightPos& lightPosition : lightPositions) {
+        ComputeSingleLightDosageMap(lightPosition, photonsPerLight, mesh->triangleCount);
+    }
+}
+
+uint32_t RayTracer::SeedAfter(const float3& lp)
+{
+    if (seedQueueHead < seedQueue.size()) {
+        const float* q = &seedQueuePos[3 * seedQueueHead];
+        if (!memcmp(&q[0], &lp.x, 4) && !memcmp(&q[1], &lp.y, 4) && !memcmp(&q[2], &lp.z, 4))
+            return seedQueue[seedQueueHead++];
+        seedQueue.clear();   // the route changed under us: fall back to one launch at a time
+        seedQueueHead = 0;
+    }
+    float pos[3] = {lp.x, lp.y, lp.z};
+    uint32_t seeds[2] = {seedState, seedState};
+    Check(uvrt_seed_chain(ctx, pos, 1, lightLength, seedState, seeds), "seed_chain");
+    return seeds[1];
+}
+
+// photonsPerLight and triangleCount are parameters because CalibratePower() uses its own values.
+// (triangleCount only sized the reference's accumulate launch; the backend knows the scene size.)
+void RayTracer::ComputeSingleLightDosageMap(LightPos lightPos, int photonsPerLight, int /*triangleCount*/)
+{
+    if (!ok) return;
+    float3 lightposition = make_float3(lightPos.position.x, mesh->floorHeight + lightHeight, lightPos.position.y);
+    const bool mine = shardCount <= 1 || (launchCounter % shardCount) == shardRank;
+    if (mine) {
+        if (!Check(uvrt_trace(ctx, lightposition.x, lightposition.y, lightposition.z, lightLength, lightPos.duration, 0,
+                              photonsPerLight, seedState),
+                   "trace"))
+            return;
+        raysTraced += photonsPerLight;
+    }
+    seedState = SeedAfter(lightposition);
+    launchCounter++;
+    photonMapSize += photonsPerLight;
+}
+
+// Photon counts -> dose or irradiance -> heat-map colours (raytracer.cpp:93-120)
+void RayTracer::Shade()
+{
+    if (!ok) return;
+    if (viewMode == maxpower) {
+        // photons of a single launch; x100: W/m^2 -> microW/cm^2
+        if (!Check(uvrt_shade(ctx, 1, photonsPerLight, lightIntensity * 100), "shade")) return;
+        Check(uvrt_color(ctx, minPower, thresholdView), "color");
+    } else {
+        // every photon carries 1/(photons per light) of one lamp's power; x0.1: J/m^2 -> mJ/cm^2
+        int perLight = lightPositions.empty() ? 0 : photonMapSize / (int)lightPositions.size();
+        if (!Check(uvrt_shade(ctx, 0, perLight, lightIntensity * 0.1f), "shade")) return;
+        Check(uvrt_color(ctx, minDosage, thresholdView), "color");
+    }
+}
+
+void RayTracer::Reduce()
+{
+    if (!ok) return;
+    Check(uvrt_reduce(ctx), "reduce");
+}
+
+const float* RayTracer::ReadDosageMap()
+{
+    if (!ok || !mesh) return dosageMap;
+    if (dosageMapSize < mesh->triangleCount) {
+        delete[] dosageMap;
+        dosageMapSize = mesh->triangleCount;
+        dosageMap = new float[dosageMapSize];
+    }
+    Check(uvrt_read(ctx, UVRT_BUF_DOSE, dosageMap, sizeof(float) * (size_t)mesh->triangleCount), "read dose");
+    return dosageMap;
+}
+
+void RayTracer::ResetDosageMap()
+{
+    startedComputation = true;
+    compTime = 0;
+    timerClock.reset();
+    if (saveRouteOnReset) SaveRoute(defaultRouteFile);
+    progress = 0;
+    finishedComputation = false;
+    currIterations = 0;
+    launchCounter = 0;
+    raysTraced = 0;
+    ClearBuffers(true);
+}
+
+void RayTracer::ClearBuffers(bool resetColor)
+{
+    photonMapSize = 0;
+    if (!ok) return;
+    // the reference also reallocates its 32*photonCount-byte ray buffer here (raytracer.cpp:137);
+    // the backend sizes its ray buffer by the largest launch instead
+    Check(uvrt_reset(ctx, resetColor ? 1 : 0), "reset");
+}
+
+// Scales lightIntensity so that the simulated irradiance on a 0.2 m square at measureDist matches
+// a measured value (raytracer.cpp:151-227).
+void RayTracer::CalibratePower(float measurePower, float measureHeight, float measureDist)
+{
+    if (!ok) return;
+    measureHeight += mesh->floorHeight;
+    LightPos singleLightPos;
+    singleLightPos.position = make_float2(0.0f, 0.0f);
+    singleLightPos.duration = 0;
+    const float w = 0.1f;
+    const float px = singleLightPos.position.x, pz = singleLightPos.position.y + measureDist;
+    Tri square[2];
+    memset(square, 0, sizeof square);
+    square[0].vertex0 = make_float3_strict(px + w, measureHeight + w, pz);
+    square[0].vertex1 = make_float3_strict(px - w, measureHeight + w, pz);
+    square[0].vertex2 = make_float3_strict(px + w, measureHeight - w, pz);
+    square[1].vertex0 = make_float3_strict(px - w, measureHeight - w, pz);
+    square[1].vertex1 = make_float3_strict(px - w, measureHeight + w, pz);
+    square[1].vertex2 = make_float3_strict(px + w, measureHeight - w, pz);
+    BVHNode hostNode;
+    memset(&hostNode, 0, sizeof hostNode);
+    hostNode.leftFirst = 0;
+    hostNode.triCount = 2;     // a single leaf; its box is never tested
+    uint hostTriIdx[2] = {0, 1};
+    if (!Check(uvrt_upload_scene(ctx, square, 2, &hostNode, 1, hostTriIdx), "upload calibration scene")) return;
+
+    ClearBuffers(false);
+
+    const int savedCount = shardCount;
+    shardCount = 1;            // every rank calibrates on its own
+    for (int i = 0; i < maxIterations; ++i) {
+        ComputeSingleLightDosageMap(singleLightPos, photonCount, 2);
+    }
+    shardCount = savedCount;
+
+    // power 1, so that measured / simulated irradiance is the calibrated power
+    float two[2] = {0, 0};
+    if (Check(uvrt_shade(ctx, 1, photonCount, 1.0f), "shade") &&
+        Check(uvrt_read(ctx, UVRT_BUF_DOSE, two, sizeof two), "read dose")) {
+        dosageMap[0] = two[0];
+        dosageMap[1] = two[1];
+        float avgPower = (dosageMap[0] + dosageMap[1]) / 2.0f;
+        calibratedPower = 0.01f * (measurePower / avgPower);
+        lightIntensity = calibratedPower;
+    }
+    UploadScene();             // back to the room (per-triangle buffers are zeroed)
+    photonMapSize = 0;
+    std::cout << "Done calibrating " << std::endl;
+}
+
+static std::string RoutePath(const char* fileName)
+{
+    return AssetRoot() + "positions/" + fileName + ".xml";
+}
+
+void RayTracer::SaveRoute(char fileName[32])
+{
+    using uvrt_xml::Element;
+    Element root;
+    root.name = "route";
+    root.add("aantal_fotonen")->text = std::to_string(photonCount);
+    root.add("aantal_iteraties")->text = std::to_string(maxIterations);
+    root.add("lamp_sterkte")->text = uvrt_xml::fmt_float(lightIntensity);
+    root.add("minimale_dosis")->text = uvrt_xml::fmt_float(minDosage);
+    root.add("minimale_bestralingssterkte")->text = uvrt_xml::fmt_float(minPower);
+    root.add("lamp_lengte")->text = uvrt_xml::fmt_float(lightLength);
+    root.add("lamp_hoogte")->text = uvrt_xml::fmt_float(lightHeight);
+    Element* route = root.add("route");
+    for (size_t i = 0; i < lightPositions.size(); i++) {
+        Element* e = route->add("lamp_positie_" + std::to_string(i));
+        e->attrs.emplace_back("positie_x", uvrt_xml::fmt_float(lightPositions[i].position.x));
+        e->attrs.emplace_back("positie_y", uvrt_xml::fmt_float(lightPositions[i].position.y));
+        e->attrs.emplace_back("duration", uvrt_xml::fmt_float(lightPositions[i].duration));
+    }
+    std::string out;
+    uvrt_xml::write(root, out, 0);
+    std::ofstream f(RoutePath(fileName), std::ios::binary);
+    if (f) f << out;
+}
+
+void RayTracer::LoadRoute(char fileName[32])
+{
+    std::ifstream f(RoutePath(fileName), std::ios::binary);
+    if (!f) return;   // like the reference: a missing or broken file leaves the settings alone
+    std::stringstream ss;
+    ss << f.rdbuf();
+    std::unique_ptr<uvrt_xml::Element> root = uvrt_xml::Reader(ss.str()).parse();
+    if (!root) return;
+    uvrt_xml::Element* e;
+    if ((e = root->child("aantal_fotonen"))) e->int_text(&photonCount);
+    if ((e = root->child("aantal_iteraties"))) e->int_text(&maxIterations);
+    if ((e = root->child("lamp_sterkte"))) e->float_text(&lightIntensity);
+    if ((e = root->child("minimale_dosis"))) e->float_text(&minDosage);
+    if ((e = root->child("minimale_bestralingssterkte"))) e->float_text(&minPower);
+    if ((e = root->child("lamp_lengte"))) e->float_text(&lightLength);
+    if ((e = root->child("lamp_hoogte"))) e->float_text(&lightHeight);
+    if ((e = root->child("route"))) {
+        lightPositions.clear();
+        // positions are looked up by consecutive index until one is missing (raytracer.cpp:285-297)
+        for (int i = 0;; i++) {
+            uvrt_xml::Element* p = e->child("lamp_positie_" + std::to_string(i));
+            if (!p) break;
+            LightPos lp;
+            lp.position = make_float2(0.0f, 0.0f);
+            lp.duration = 0.0f;
+            p->float_attr("positie_x", &lp.position.x);
+            p->float_attr("positie_y", &lp.position.y);
+            p->float_attr("duration", &lp.duration);
+            lightPositions.push_back(lp);
+        }
+    }
+    UpdatePhotonsPerLight();
+}
+
+} // namespace Tmpl8

@@ -1,0 +1,94 @@
+// raytracer.h -- the simulation driver with the reference's public surface
+// (raytracer.h:5-59 of the reference: same methods, same tunable fields), re-hosted on the
+// libuvrt C ABI (include/uvrt.h) instead of the OpenCL Kernel/Buffer wrapper.
+#pragma once
+
+struct uvrt_ctx;
+
+namespace Tmpl8 {
+
+struct LightPos {
+    float2 position;
+    float duration;
+};
+
+enum ViewMode { dosage, maxpower, texture };
+
+class RayTracer {
+public:
+    RayTracer() = default;
+    ~RayTracer();
+    RayTracer(const RayTracer&) = delete;
+    RayTracer& operator=(const RayTracer&) = delete;
+
+    // ---- the reference's interface (raytracer.h:16-26) ----
+    void Init(Mesh* mesh);
+    void UpdatePhotonsPerLight();
+    void ComputeDosageMap();
+    void ComputeSingleLightDosageMap(LightPos lightPos, int photonsPerLight, int triangleCount);
+    void Shade();
+    void ResetDosageMap();
+    void ClearBuffers(bool resetColor);
+    void AddLamp();
+    void CalibratePower(float measurePower, float measureHeight, float measureDist);
+    void SaveRoute(char fileName[32]);
+    void LoadRoute(char fileName[32]);
+
+    float lightLength = 1.0f;
+    float lightHeight = 0.8f;
+    int maxPhotonCount = (1 << 26);
+    int photonCount = (1 << 25);
+    int maxIterations = 10;
+    int currIterations = 0; // The number of computed iterations
+    float lightIntensity = 450;
+    float minDosage = 100, minPower = 1500;
+    char defaultRouteFile[32] = "route";
+    char newRouteFile[32] = "new_route";
+
+    Mesh* mesh = 0;
+    float* dosageMap = new float[2];
+    std::vector<LightPos> lightPositions;
+    int photonsPerLight = 0; // The number of photons per light of a single iteration
+    float compTime = 0;
+    float progressTextTimer = 0;
+    float progress = 0;
+    Timer timerClock;
+    bool finishedComputation = true;
+    ViewMode viewMode = texture;
+    bool thresholdView = false;
+    bool startedComputation = false;
+    float calibratedPower = 0;
+    int photonMapSize = 0;
+
+    // ---- additions (no counterpart in the reference) ----
+    int device = 0;              // CUDA device used by Init()
+    uvrt_ctx* ctx = 0;           // backend context (replaces the Kernel*/Buffer* members)
+    bool ok = true;              // false after a backend failure; see lastError
+    std::string lastError;
+    bool saveRouteOnReset = true; // the reference rewrites positions/<route>.xml on every run start
+    // Device-side SEED of generate.cl:6 as seen by the next launch: starts at 0
+    // and, like the reference's program-scope variable, survives ResetDosageMap().
+    uint32_t seedState = 0;
+    // Work sharing between GPUs: launch k (counted over the whole run) is traced by the rank with
+    // k % shardCount == shardRank; every rank advances seedState and photonMapSize for every launch.
+    int shardRank = 0, shardCount = 1;
+    long long launchCounter = 0;
+    // Cross-rank sum (photon map) and max (max map); needs uvrt_comm_init on ctx.  Call once,
+    // after the last ComputeDosageMap() and before Shade().
+    void Reduce();
+    // Copies the per-triangle dose (after Shade) into dosageMap, resized to triangleCount floats.
+    const float* ReadDosageMap();
+    int64_t RaysTraced() const { return raysTraced; }
+
+private:
+    bool Check(int rc, const char* what);
+    void UploadScene();
+    uint32_t SeedAfter(const float3& lightposition);
+    std::vector<uint32_t> seedQueue;        // precomputed SEED values for the next launches
+    std::vector<float> seedQueuePos;        // their lamp positions (xyz), to validate the queue
+    size_t seedQueueHead = 0;
+    int dosageMapSize = 2;
+    int64_t raysTraced = 0;
+};
+
+} // namespace Tmpl8

@@ -1,0 +1,173 @@
+"""Host-side drop-in classes (Mesh loader, BVH builder, route files) and the C ABI surface.
+CPU only: nothing here launches a kernel."""
+import ctypes as C
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import uvrt_testlib as T
+
+REF_ROOT = "/root/reference"
+
+
+def test_libraries_export_every_declared_symbol(uv):
+    L, H = uv.lib(), uv.host()
+    names = uv.declared_symbols("uvrt.h")
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"libuvrt.so does not export {n}"
+    hnames = [n for n in uv.declared_symbols("uvrt_host.h") if n.startswith(("uvrt_sim_", "uvrt_host_"))]
+    assert len(hnames) >= 25
+    for n in hnames:
+        assert hasattr(H, n), f"libuvrt_host.so does not export {n}"
+    assert b"sm_100a" in L.uvrt_version()
+
+
+def test_no_device_is_a_loud_error_not_a_fallback(uv):
+    n = C.c_int(-1)
+    rc = uv.lib().uvrt_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(uv.UvrtError) as e:
+        uv.Context()
+    assert e.value.code == -6 and "no CPU fallback" in str(e.value)
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_mesh("testroomopt")
+    with pytest.raises(uv.UvrtError):
+        sim.init("route")
+
+
+def test_glb_loader_matches_independent_reader(room):
+    tris, nodes, tri_idx, floor = room
+    want = T.load_glb_tris(T.ROOM)
+    assert tris.shape == want.shape == (44866, 16)
+    for c in (0, 4, 8):
+        assert np.array_equal(tris[:, c:c + 3].view(np.uint32), want[:, c:c + 3].view(np.uint32))
+    assert np.float32(floor) == T.floor_height(want)
+    assert abs(float(floor) - (-1.3954836)) < 1e-7
+
+
+def test_loader_errors_are_reported(uv, tmp_path):
+    os.makedirs(tmp_path / "rooms")
+    (tmp_path / "rooms" / "bad.glb").write_bytes(b"not a glb at all")
+    blob = open(T.ROOM, "rb").read()
+    (tmp_path / "rooms" / "cut.glb").write_bytes(blob[: len(blob) // 2])
+    sim = uv.Sim(asset_root=str(tmp_path))
+    for name in ("missing", "bad", "cut"):
+        with pytest.raises(uv.UvrtError):
+            sim.load_mesh(name)
+    # the sim is still usable afterwards
+    shutil.copy(T.ROOM, tmp_path / "rooms" / "ok.glb")
+    sim.load_mesh("ok")
+    assert sim.mesh_info()["triangles"] == 44866
+    uv.Sim(asset_root=T.DATA)  # restore the asset root for later tests
+
+
+def test_bvh_fingerprint_matches_golden(room, golden):
+    tris, nodes, tri_idx, _ = room
+    g = golden["scene"]
+    assert tris.shape[0] == g["triangles"]
+    assert [int(x) for x in tri_idx[:8]] == g["triIdx_head"]
+    assert f"{T.fnv(tri_idx):016x}" == g["fnv_triIdx"]
+    pre = T.reachable_preorder(nodes)
+    assert len(pre) == g["reachable_nodes"] and int(pre.max()) == g["max_node_index"]
+    buf = bytearray()
+    for i in pre:
+        buf += np.uint32(i).tobytes() + nodes[i].tobytes()
+    assert f"{T.fnv(np.frombuffer(bytes(buf), dtype=np.uint8)):016x}" == g["fnv_nodes_preorder"]
+    # nodesUsed covers the whole tree (the reference reports 2N = 89,732 < 89,746: App. B-3)
+    assert len(nodes) == g["max_node_index"] + 1 > 2 * g["triangles"]
+
+
+def _check_tree(tris, nodes, tri_idx):
+    n = tris.shape[0]
+    seen = np.zeros(n, dtype=np.int32)
+    stack = [0]
+    while stack:
+        i = stack.pop()
+        nd = nodes[i]
+        if nd["triCount"] > 0:
+            ids = tri_idx[nd["leftFirst"]: nd["leftFirst"] + nd["triCount"]]
+            seen[ids] += 1
+            v = tris[ids][:, [0, 1, 2, 4, 5, 6, 8, 9, 10]].reshape(-1, 3)
+            assert np.all(v >= nd["min"]) and np.all(v <= nd["max"])
+        else:
+            for c in (nd["leftFirst"], nd["leftFirst"] + 1):
+                assert np.all(nodes[c]["min"] >= nd["min"]) and np.all(nodes[c]["max"] <= nd["max"])
+                stack.append(int(c))
+    assert np.all(seen == 1), "every triangle must sit in exactly one leaf"
+
+
+def test_bvh_structure(room):
+    _check_tree(*room[:3])
+
+
+def test_bvh_equals_reference_builder_on_other_meshes(uv, checkers):
+    if not checkers.ref_available():
+        pytest.skip("oracle/_ref not built")
+    from importlib import import_module
+    B = import_module("small-project-uv-robot-ray-tracer_b200.binding")
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 17, 200, 5000):
+        tris = np.zeros((n, 16), dtype=np.float32)
+        c = rng.uniform(-5, 5, (n, 3))
+        for k in range(3):
+            tris[:, 4 * k: 4 * k + 3] = (c + rng.uniform(-0.2, 0.2, (n, 3))).astype(np.float32)
+        if n >= 17:
+            tris[5] = tris[6]          # duplicate triangles: identical centroids
+            tris[7, 0:12] = tris[7, 0]  # degenerate
+        mt, mn, mi = B.build_bvh(tris)
+        rt, rn, ri = T.ref_build_bvh(tris)
+        assert np.array_equal(mi, ri)
+        assert mt.tobytes() == rt.tobytes()
+        pre = T.reachable_preorder(rn)
+        assert np.array_equal(pre, T.reachable_preorder(mn))
+        assert rn[pre].tobytes() == mn[pre].tobytes()
+        _check_tree(mt, mn, mi)
+
+
+@pytest.mark.parametrize("name", ["route", "lange_route"])
+def test_route_files(uv, tmp_path, name):
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_route(name)
+    p = sim.params
+    assert (p.photonCount, p.maxIterations, p.photonsPerLight) == (33554432, 10, 2796202)
+    assert p.lightLength == 1.0
+    want = {"route": (443.31842, 0.60000002, 300.0), "lange_route": (440.19705, 0.40000001, 100.0)}[name]
+    assert (np.float32(p.lightIntensity), np.float32(p.lightHeight), np.float32(p.minDosage)) == tuple(np.float32(w) for w in want)
+    pos = sim.positions
+    assert pos.shape == (12, 3) and np.all(pos[:, 2] == 60)
+    assert pos[0, 0] == np.float32(-0.25500134) and pos[0, 1] == np.float32(-3.3149862)
+    # write it back: same bytes as the file the reference's tinyxml2 writer produced
+    os.makedirs(tmp_path / "positions")
+    sim2 = uv.Sim(asset_root=str(tmp_path))
+    sim2.set_positions(pos)
+    sim2.set_params(photonCount=p.photonCount, maxIterations=p.maxIterations, lightIntensity=p.lightIntensity,
+                    minDosage=p.minDosage, minPower=p.minPower, lightLength=p.lightLength, lightHeight=p.lightHeight)
+    sim2.save_route("copy")
+    mine = (tmp_path / "positions" / "copy.xml").read_bytes()
+    assert mine == open(os.path.join(T.DATA, "positions", name + ".xml"), "rb").read()
+    if os.path.isdir(REF_ROOT):
+        assert mine == open(os.path.join(REF_ROOT, "positions", name + ".xml"), "rb").read()
+    uv.Sim(asset_root=T.DATA)
+
+
+def test_route_missing_or_broken_file_keeps_settings(uv, tmp_path):
+    os.makedirs(tmp_path / "positions")
+    (tmp_path / "positions" / "broken.xml").write_text("<route><aantal_fotonen>12")
+    (tmp_path / "positions" / "partial.xml").write_text(
+        "<?xml version='1.0'?><!-- c --><route><aantal_fotonen>1000</aantal_fotonen><route>"
+        "<lamp_positie_0 positie_x='1.5' positie_y='-2' duration='3'/><lamp_positie_2 positie_x='9'/></route></route>")
+    sim = uv.Sim(asset_root=str(tmp_path))
+    before = sim.params.photonCount
+    sim.load_route("nope")
+    sim.load_route("broken")
+    assert sim.params.photonCount == before and len(sim.positions) == 0
+    sim.load_route("partial")
+    assert sim.params.photonCount == 1000
+    # positions are read by consecutive index: lamp_positie_2 without _1 is not reached
+    assert sim.positions.tolist() == [[1.5, -2.0, 3.0]]
+    assert sim.params.photonsPerLight == 1000
+    uv.Sim(asset_root=T.DATA)
