@@ -141,6 +141,11 @@ int64_t uvrt_launch_count(const uvrt_ctx* ctx);
 /* Event timing on the context's stream (torch.cuda.Event only sees torch's stream). */
 int uvrt_mark(uvrt_ctx* ctx, int slot);                       /* slot 0..15 */
 int uvrt_elapsed_ms(uvrt_ctx* ctx, int slotStart, int slotStop, float* ms); /* synchronises */
+/* Overwrites a scratch buffer larger than the L2 (256 MiB) on the context's stream, so that the
+ * next launch starts from a cold L2 (benchmark hygiene). */
+int uvrt_flush_l2(uvrt_ctx* ctx);
+/* Bytes the last uvrt_upload_scene copied host -> device. */
+int64_t uvrt_scene_upload_bytes(const uvrt_ctx* ctx);
 /* Traversal statistics of the repacked scene: inner nodes, leaves, depth, stack bound. */
 int uvrt_scene_info(uvrt_ctx* ctx, int* innerNodes, int* leaves, int* depth, int* stackEntries);
 

@@ -111,6 +111,8 @@ def lib():
         "uvrt_elapsed_ms": (i, [vp, i, i, C.POINTER(f)]),
         "uvrt_scene_info": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
         "uvrt_selftest_division": (i, [vp, i, i, vp]),
+        "uvrt_flush_l2": (i, [vp]),
+        "uvrt_scene_upload_bytes": (i64, [vp]),
         "uvrt_version": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
@@ -288,6 +290,12 @@ class Context:
     def stage_time_reset(self):
         self.check(self.L.uvrt_stage_time_reset(self.h))
 
+    def flush_l2(self):
+        self.check(self.L.uvrt_flush_l2(self.h))
+
+    def scene_upload_bytes(self):
+        return int(self.L.uvrt_scene_upload_bytes(self.h))
+
     def launch_count(self):
         return int(self.L.uvrt_launch_count(self.h))
 
@@ -406,7 +414,9 @@ class Sim:
 
     @property
     def ctx(self):
-        return Context(handle=C.c_void_p(self.H.uvrt_sim_ctx(self.h)))
+        c = Context(handle=C.c_void_p(self.H.uvrt_sim_ctx(self.h)))
+        c.n_tris = self.mesh_info()["triangles"]
+        return c
 
     def reset_dosage_map(self):
         self.check(self.H.uvrt_sim_reset_dosage_map(self.h))

@@ -89,7 +89,7 @@ struct uvrt_ctx {
     uint32_t rootRef = 0;
     int sceneTame = 0;
     float4* dPairs = nullptr;   // nPairs x 4 float4
-    float4* dWtris = nullptr;   // nTris  x 3 float4 (leaf order)
+    float4* dWtris = nullptr;   // nTris  x 4 float4 (leaf order: v0+tag, edge1, edge2, pad)
     float4* dVerts = nullptr;   // nTris  x 4 float4 (reference order and layout)
     // per-triangle state (raytracer.h:54-55)
     int* dCounts = nullptr;
@@ -105,15 +105,32 @@ struct uvrt_ctx {
     uint32_t* dSeeds = nullptr;
     float* dSeedPos = nullptr;
     int seedCap = 0;
-    // pinned staging for the scene upload
+    void* dFlush = nullptr;              // L2 flush scratch
+    // ray binning (counting sort by direction / origin cell)
+    unsigned int* dBinCount = nullptr;
+    unsigned int* dBinStart = nullptr;
+    int binCap = 0;
+    uint2* dKeyRank = nullptr;
+    uint32_t* dPerm = nullptr;
+    long long permCap = 0;
+    int binRays = 1, binY = 8, binT = 32, binP = 64;
+    float binY0 = 0.0f, binLen = 1.0f;   // lamp extent of the rays in the buffer
+    bool binExtentKnown = false;
+    int64_t uploadBytes = 0;
+    // pinned staging for the scene upload, and scratch that survives between uploads
     void* hStage = nullptr;
     size_t hStageBytes = 0;
+    size_t pairCap = 0, wtriCap = 0;     // device capacities in bytes
+    std::vector<int32_t> upId;
+    std::vector<uint32_t> upOrder;
 
     // options
     int extendVariant = -1;   // -1: default
     int stageTiming = 0;
     int histMode = 0;
     int blocksPerSm = 0;      // 0: default for the variant
+    int simpleCfg = 1;        // 128 threads, <= 40 registers (48 resident warps per SM): fastest in the sweep
+    int refill = 24;          // persistent kernels: refill when fewer lanes than this are busy
 
     // measurement
     std::vector<TimedLaunch> timed;
@@ -237,21 +254,35 @@ inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block 
 //   2  simple / Markstein one-step
 //   10 + 3*k + d  persistent, K = {1, 2, 4, 8, inf}[k], d = {IEEE, M2, M1}
 constexpr int kStack = 64;
-constexpr int kDefaultVariant = 1;
+constexpr int kDefaultVariant = 2;   // one thread per ray, one-step shared-reciprocal division (proven exact)
 
-template <int DIV>
-void launch_simple(uvrt_ctx* ctx, long long nRays)
+template <int DIV, int THREADS, int MINB>
+void launch_simple_cfg(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
-    k_extend_simple<DIV, kStack><<<grid_for(nRays, 128), 128, 0, ctx->stream>>>(
-        ctx->dCounts, ctx->dWtris, ctx->dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame);
+    k_extend_simple<DIV, kStack, THREADS, MINB><<<grid_for(nRays, THREADS), THREADS, 0, ctx->stream>>>(
+        ctx->dCounts, ctx->dWtris, ctx->dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm);
 }
 
-template <int DIV, int K, int HIST>
-void launch_persist(uvrt_ctx* ctx, long long nRays)
+template <int DIV>
+void launch_simple(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
+{
+    // "simple_cfg": block size / resident-blocks hint (register cap) of the one-thread-per-ray kernel
+    switch (ctx->simpleCfg) {
+    case 1: launch_simple_cfg<DIV, 128, 12>(ctx, nRays, perm); break;   // <= 40 registers: 48 warps/SM
+    case 2: launch_simple_cfg<DIV, 128, 16>(ctx, nRays, perm); break;   // <= 32 registers: 64 warps/SM
+    case 3: launch_simple_cfg<DIV, 64, 20>(ctx, nRays, perm); break;
+    case 4: launch_simple_cfg<DIV, 256, 5>(ctx, nRays, perm); break;
+    case 5: launch_simple_cfg<DIV, 32, 32>(ctx, nRays, perm); break;
+    default: launch_simple_cfg<DIV, 128, 1>(ctx, nRays, perm); break;
+    }
+}
+
+template <int DIV, int K, int HIST, int REFILL>
+void launch_persist_r(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
     constexpr int THREADS = 128;
     constexpr int MINB = 4;
-    auto kern = k_extend_persist<DIV, kStack, K, 24, HIST, THREADS, MINB>;
+    auto kern = k_extend_persist<DIV, kStack, K, REFILL, HIST, THREADS, MINB>;
     int perSm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, THREADS, 0);
     if (perSm < 1) perSm = 1;
@@ -261,38 +292,96 @@ void launch_persist(uvrt_ctx* ctx, long long nRays)
     if (blocks > needed) blocks = needed;
     cudaMemsetAsync(ctx->dQueue, 0, sizeof(unsigned int), ctx->stream);
     kern<<<(unsigned)blocks, THREADS, 0, ctx->stream>>>(ctx->dCounts, ctx->dWtris, ctx->dRays, ctx->dPairs,
-                                                        ctx->rootRef, (uint32_t)nRays, ctx->sceneTame, ctx->dQueue);
+                                                        ctx->rootRef, (uint32_t)nRays, ctx->sceneTame, ctx->dQueue, perm);
+}
+
+template <int DIV, int K, int HIST>
+void launch_persist(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
+{
+    // refill threshold: 0 = a warp takes 32 new rays only when all of its lanes are done
+    if (HIST || ctx->refill >= 24) launch_persist_r<DIV, K, HIST, 24>(ctx, nRays, perm);
+    else if (ctx->refill >= 8) launch_persist_r<DIV, K, 0, 8>(ctx, nRays, perm);
+    else launch_persist_r<DIV, K, 0, 0>(ctx, nRays, perm);
 }
 
 template <int DIV, int K>
-void launch_persist_h(uvrt_ctx* ctx, long long nRays)
+void launch_persist_h(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
-    if (ctx->histMode) launch_persist<DIV, K, 1>(ctx, nRays);
-    else launch_persist<DIV, K, 0>(ctx, nRays);
+    if (ctx->histMode) launch_persist<DIV, K, 1>(ctx, nRays, perm);
+    else launch_persist<DIV, K, 0>(ctx, nRays, perm);
 }
 
 template <int K>
-void launch_persist_d(uvrt_ctx* ctx, long long nRays, int d)
+void launch_persist_d(uvrt_ctx* ctx, long long nRays, int d, const uint32_t* perm)
 {
-    if (d == 0) launch_persist_h<DIV_IEEE, K>(ctx, nRays);
-    else if (d == 1) launch_persist_h<DIV_MARKSTEIN2, K>(ctx, nRays);
-    else launch_persist_h<DIV_MARKSTEIN1, K>(ctx, nRays);
+    if (d == 0) launch_persist_h<DIV_IEEE, K>(ctx, nRays, perm);
+    else if (d == 1) launch_persist_h<DIV_MARKSTEIN2, K>(ctx, nRays, perm);
+    else launch_persist_h<DIV_MARKSTEIN1, K>(ctx, nRays, perm);
 }
 
-int launch_extend(uvrt_ctx* ctx, long long nRays)
+// Counting sort of the ray queue by (origin slice, dir.y cell, azimuth cell); fills ctx->dPerm.
+int bin_rays(uvrt_ctx* ctx, long long nRays)
+{
+    // the scan kernel handles 4096 * VEC counters; the table is padded up to the next supported size
+    const int wanted = ctx->binY * ctx->binT * ctx->binP;
+    int nBins = 4096;
+    while (nBins < wanted) nBins *= 2;
+    if (nBins > (4096 << 4))
+        return fail(ctx, UVRT_ERR_INVALID, "bin_y*bin_t*bin_p = %d exceeds the supported %d bins", wanted, 4096 << 4);
+    if (nBins > ctx->binCap) {
+        if (ctx->dBinCount) cudaFree(ctx->dBinCount);
+        if (ctx->dBinStart) cudaFree(ctx->dBinStart);
+        ctx->dBinCount = ctx->dBinStart = nullptr;
+        ctx->binCap = 0;
+        CK(cudaMalloc((void**)&ctx->dBinCount, (size_t)nBins * 4));
+        CK(cudaMalloc((void**)&ctx->dBinStart, (size_t)nBins * 4));
+        CK(cudaMemsetAsync(ctx->dBinCount, 0, (size_t)nBins * 4, ctx->stream));
+        ctx->binCap = nBins;
+    }
+    if (nRays > ctx->permCap) {
+        if (ctx->dKeyRank) cudaFree(ctx->dKeyRank);
+        if (ctx->dPerm) cudaFree(ctx->dPerm);
+        ctx->dKeyRank = nullptr; ctx->dPerm = nullptr; ctx->permCap = 0;
+        CK(cudaMalloc((void**)&ctx->dKeyRank, (size_t)ctx->rayCap * 8));
+        CK(cudaMalloc((void**)&ctx->dPerm, (size_t)ctx->rayCap * 4));
+        ctx->permCap = ctx->rayCap;
+    }
+    BinDims d;
+    d.nY = ctx->binExtentKnown ? ctx->binY : 1;
+    d.nT = ctx->binT;
+    d.nP = ctx->binP;
+    d.y0 = ctx->binY0;
+    d.invLen = ctx->binLen > 0.0f ? 1.0f / ctx->binLen : 0.0f;
+    StageTimer t(ctx, UVRT_STAGE_BIN);
+    k_bin_count<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dRays, (uint32_t)nRays, d, ctx->dBinCount, ctx->dKeyRank);
+    uint4* bc = reinterpret_cast<uint4*>(ctx->dBinCount);
+    uint4* bs = reinterpret_cast<uint4*>(ctx->dBinStart);
+    switch (nBins / 4096) {
+    case 1: k_bin_scan<1><<<1, 1024, 0, ctx->stream>>>(bc, bs); break;
+    case 2: k_bin_scan<2><<<1, 1024, 0, ctx->stream>>>(bc, bs); break;
+    case 4: k_bin_scan<4><<<1, 1024, 0, ctx->stream>>>(bc, bs); break;
+    case 8: k_bin_scan<8><<<1, 1024, 0, ctx->stream>>>(bc, bs); break;
+    default: k_bin_scan<16><<<1, 1024, 0, ctx->stream>>>(bc, bs); break;
+    }
+    k_bin_scatter<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dKeyRank, ctx->dBinStart, (uint32_t)nRays, ctx->dPerm);
+    ctx->launches += 3;
+    return UVRT_OK;
+}
+
+int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
     int v = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
-    if (v == 0) launch_simple<DIV_IEEE>(ctx, nRays);
-    else if (v == 1) launch_simple<DIV_MARKSTEIN2>(ctx, nRays);
-    else if (v == 2) launch_simple<DIV_MARKSTEIN1>(ctx, nRays);
+    if (v == 0) launch_simple<DIV_IEEE>(ctx, nRays, perm);
+    else if (v == 1) launch_simple<DIV_MARKSTEIN2>(ctx, nRays, perm);
+    else if (v == 2) launch_simple<DIV_MARKSTEIN1>(ctx, nRays, perm);
     else if (v >= 10 && v < 25) {
         int k = (v - 10) / 3, d = (v - 10) % 3;
         switch (k) {
-        case 0: launch_persist_d<1>(ctx, nRays, d); break;
-        case 1: launch_persist_d<2>(ctx, nRays, d); break;
-        case 2: launch_persist_d<4>(ctx, nRays, d); break;
-        case 3: launch_persist_d<8>(ctx, nRays, d); break;
-        default: launch_persist_d<(1 << 30)>(ctx, nRays, d); break;
+        case 0: launch_persist_d<1>(ctx, nRays, d, perm); break;
+        case 1: launch_persist_d<2>(ctx, nRays, d, perm); break;
+        case 2: launch_persist_d<4>(ctx, nRays, d, perm); break;
+        case 3: launch_persist_d<8>(ctx, nRays, d, perm); break;
+        default: launch_persist_d<16>(ctx, nRays, d, perm); break;
         }
     } else
         return fail(ctx, UVRT_ERR_INVALID, "unknown extend_variant %d", v);
@@ -359,7 +448,8 @@ void uvrt_destroy(uvrt_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     void* ptrs[] = {ctx->dPairs, ctx->dWtris, ctx->dVerts, ctx->dCounts, ctx->dSum, ctx->dMax, ctx->dDose,
-                    ctx->dColor, ctx->dRays, ctx->dQueue, ctx->dSeeds, ctx->dSeedPos};
+                    ctx->dColor, ctx->dRays, ctx->dQueue, ctx->dSeeds, ctx->dSeedPos, ctx->dFlush,
+                    ctx->dBinCount, ctx->dBinStart, ctx->dKeyRank, ctx->dPerm};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->hStage) cudaFreeHost(ctx->hStage);
     for (auto& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
@@ -392,15 +482,15 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
     const HostNode* nodes = (const HostNode*)nodesV;
 
     // ---- pass 1: walk the tree from the root, number inner nodes (pairs) and leaf slots -------
-    std::vector<int32_t> id(nNodes, -1);   // inner: pair index; leaf: first slot
-    std::vector<uint32_t> order;           // reachable nodes, pre-order, left child first
-    order.reserve((size_t)std::min<long long>(nNodes, 2ll * nTris));
+    std::vector<int32_t>& id = ctx->upId;        // inner: pair index; leaf: first slot
+    std::vector<uint32_t>& order = ctx->upOrder; // reachable nodes, pre-order, left child first
+    id.assign((size_t)nNodes, -1);
+    order.clear();
     struct Item { uint32_t node; int depth; };
     std::vector<Item> stack;
     stack.push_back({0u, 0});
     int nPairs = 0, nLeaves = 0, depth = 0;
     long long nSlots = 0;
-    std::vector<uint8_t> used(nTris, 0);
     while (!stack.empty()) {
         Item it = stack.back();
         stack.pop_back();
@@ -420,7 +510,6 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
             for (uint32_t k = 0; k < nd.triCount; k++) {
                 uint32_t t = triIdx[nd.leftFirst + k];
                 if (t >= (uint32_t)nTris) return fail(ctx, UVRT_ERR_INVALID, "upload_scene: triIdx value %u out of range", t);
-                used[t]++;
             }
             nSlots += nd.triCount;
             nLeaves++;
@@ -434,7 +523,7 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
         return fail(ctx, UVRT_ERR_INVALID, "upload_scene: BVH depth %d exceeds the traversal stack (%d)", depth, kStack);
 
     // ---- pass 2: fill the staging image --------------------------------------------------------
-    size_t pairBytes = (size_t)std::max(nPairs, 1) * 64, wtriBytes = (size_t)std::max<long long>(nSlots, 1) * 48,
+    size_t pairBytes = (size_t)std::max(nPairs, 1) * 64, wtriBytes = (size_t)std::max<long long>(nSlots, 1) * 64,
            vertBytes = (size_t)nTris * 64;
     size_t total = pairBytes + wtriBytes + vertBytes;
     if (ctx->hStageBytes < total) {
@@ -458,13 +547,14 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
             for (uint32_t k = 0; k < nd.triCount; k++) {
                 uint32_t t = triIdx[nd.leftFirst + k];
                 const float* v = tris[t].v;
-                float* w = hw + ((size_t)id[n] + k) * 12;
+                float* w = hw + ((size_t)id[n] + k) * 16;
                 w[0] = v[0]; w[1] = v[1]; w[2] = v[2];
                 uint32_t tag = t | (k + 1 == nd.triCount ? kLastFlag : 0u);
                 memcpy(&w[3], &tag, 4);
                 // edge1 = v1 - v0, edge2 = v2 - v0 (extend.cl:13): the same fp32 subtractions, hoisted
                 w[4] = v[4] - v[0]; w[5] = v[5] - v[1]; w[6] = v[6] - v[2]; w[7] = 0.0f;
                 w[8] = v[8] - v[0]; w[9] = v[9] - v[1]; w[10] = v[10] - v[2]; w[11] = 0.0f;
+                w[12] = w[13] = w[14] = w[15] = 0.0f;
             }
         } else {
             float* p = hp + (size_t)id[n] * 16;
@@ -483,8 +573,16 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
 
     // ---- device buffers -------------------------------------------------------------------------
     int rc;
-    if ((rc = dev_alloc(ctx, &ctx->dPairs, pairBytes / 16))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->dWtris, wtriBytes / 16))) return rc;
+    if (pairBytes > ctx->pairCap) {
+        ctx->pairCap = 0;
+        if ((rc = dev_alloc(ctx, &ctx->dPairs, pairBytes / 16))) return rc;
+        ctx->pairCap = pairBytes;
+    }
+    if (wtriBytes > ctx->wtriCap) {
+        ctx->wtriCap = 0;
+        if ((rc = dev_alloc(ctx, &ctx->dWtris, wtriBytes / 16))) return rc;
+        ctx->wtriCap = wtriBytes;
+    }
     if (nTris != ctx->nTris) {
         if ((rc = dev_alloc(ctx, &ctx->dVerts, (size_t)nTris * 4))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->dCounts, (size_t)nTris))) return rc;
@@ -508,6 +606,7 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
     ctx->depth = depth;
     ctx->sceneTame = tame ? 1 : 0;
     ctx->rootRef = child_ref(0);
+    ctx->uploadBytes = (int64_t)total;
     return UVRT_OK;
 }
 
@@ -555,6 +654,9 @@ int uvrt_generate(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength
     int rc = ensure_rays(ctx, nRays);
     if (rc) return rc;
     ctx->lastRays = nRays;
+    ctx->binY0 = ly;
+    ctx->binLen = lightLength;
+    ctx->binExtentKnown = true;
     if (nRays == 0) return UVRT_OK;
     {
         StageTimer t(ctx, UVRT_STAGE_GENERATE);
@@ -572,9 +674,17 @@ int uvrt_extend(uvrt_ctx* ctx, int64_t nRays)
         return fail(ctx, UVRT_ERR_INVALID, "extend: nRays=%lld exceeds the ray buffer (%lld)", (long long)nRays, ctx->rayCap);
     if (nRays == 0) return UVRT_OK;
     int rc;
+    const uint32_t* perm = nullptr;
+    // a few thousand rays are not worth three extra launches
+    if (ctx->binRays && nRays >= 65536) {
+        rc = bin_rays(ctx, nRays);
+        if (rc) return rc;
+        CK_LAUNCH("bin");
+        perm = ctx->dPerm;
+    }
     {
         StageTimer t(ctx, UVRT_STAGE_EXTEND);
-        rc = launch_extend(ctx, nRays);
+        rc = launch_extend(ctx, nRays, perm);
     }
     if (rc) return rc;
     CK_LAUNCH("extend");
@@ -680,6 +790,7 @@ int uvrt_write(uvrt_ctx* ctx, uvrt_buffer what, const void* src, size_t bytes)
         int rc = ensure_rays(ctx, (long long)((bytes + 31) / 32));
         if (rc) return rc;
         ctx->lastRays = (long long)(bytes / 32);
+        ctx->binExtentKnown = false;   // foreign rays: no origin slicing
     }
     void* p = nullptr;
     size_t cap = 0;
@@ -758,7 +869,13 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
     else if (!strcmp(key, "stage_timing")) ctx->stageTiming = value;
     else if (!strcmp(key, "hist_mode")) ctx->histMode = value;
     else if (!strcmp(key, "blocks_per_sm")) ctx->blocksPerSm = value;
-    else return fail(ctx, UVRT_ERR_INVALID, "unknown option '%s'", key);
+    else if (!strcmp(key, "refill")) ctx->refill = value;
+    else if (!strcmp(key, "simple_cfg")) ctx->simpleCfg = value;
+    else if (!strcmp(key, "bin_rays")) ctx->binRays = value;
+    else if (!strcmp(key, "bin_y") && value >= 1 && value <= 64) ctx->binY = value;
+    else if (!strcmp(key, "bin_t") && value >= 1 && value <= 1024) ctx->binT = value;
+    else if (!strcmp(key, "bin_p") && value >= 1 && value <= 1024) ctx->binP = value;
+    else return fail(ctx, UVRT_ERR_INVALID, "unknown option '%s' (or value %d out of range)", key, value);
     return UVRT_OK;
 }
 
@@ -770,6 +887,12 @@ int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value)
     else if (!strcmp(key, "hist_mode")) *value = ctx->histMode;
     else if (!strcmp(key, "blocks_per_sm")) *value = ctx->blocksPerSm;
     else if (!strcmp(key, "scene_tame")) *value = ctx->sceneTame;
+    else if (!strcmp(key, "refill")) *value = ctx->refill;
+    else if (!strcmp(key, "simple_cfg")) *value = ctx->simpleCfg;
+    else if (!strcmp(key, "bin_rays")) *value = ctx->binRays;
+    else if (!strcmp(key, "bin_y")) *value = ctx->binY;
+    else if (!strcmp(key, "bin_t")) *value = ctx->binT;
+    else if (!strcmp(key, "bin_p")) *value = ctx->binP;
     else return fail(ctx, UVRT_ERR_INVALID, "unknown option '%s'", key);
     return UVRT_OK;
 }
@@ -802,6 +925,18 @@ int uvrt_stage_time_reset(uvrt_ctx* ctx)
     ctx->timed.clear();
     return UVRT_OK;
 }
+
+int uvrt_flush_l2(uvrt_ctx* ctx)
+{
+    if (!ctx) return UVRT_ERR_INVALID;
+    Bind b(ctx);
+    const size_t bytes = 256u << 20;
+    if (!ctx->dFlush) CK(cudaMalloc(&ctx->dFlush, bytes));
+    CK(cudaMemsetAsync(ctx->dFlush, 0xA5, bytes, ctx->stream));
+    return UVRT_OK;
+}
+
+int64_t uvrt_scene_upload_bytes(const uvrt_ctx* ctx) { return ctx ? ctx->uploadBytes : 0; }
 
 int64_t uvrt_launch_count(const uvrt_ctx* ctx) { return ctx ? ctx->launches : 0; }
 

@@ -26,6 +26,27 @@ __device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); 
 __device__ __forceinline__ float clmin(float x, float y) { return y < x ? y : x; }
 __device__ __forceinline__ float clmax(float x, float y) { return x < y ? y : x; }
 
+// 32-byte read-only load (sm_100: LDG.E.256).  One instruction fetches one whole 32-byte sector
+// per lane, where two LDG.128 would each occupy the L1 data pipe for the same sector.
+struct F8 { float4 lo, hi; };
+__device__ __forceinline__ F8 ldg256(const float4* p)
+{
+    F8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+        : "l"(p));
+    return r;
+}
+// plain (coherent) 32-byte load for data written by an earlier kernel of the same stream
+__device__ __forceinline__ F8 ld256(const float4* p)
+{
+    F8 r;
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+        : "l"(p));
+    return r;
+}
+
 // ---- RNG: tools.cl:2-4 ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t wang_hash(uint32_t s)
 {
@@ -119,8 +140,10 @@ __global__ void k_seed_chain(const float* __restrict__ lightPos3, int nLaunches,
 //                   the first step makes q faithful).  Only used for rays whose direction and
 //                   origin components keep every intermediate in the normal range, everything
 //                   else takes DIV_IEEE (see ray_is_tame()).
-//   DIV_MARKSTEIN1: one correction step; equal to RN(n/d) on every input tried (2e9 random and
-//                   adversarial pairs on the CPU, the on-device self-test) but without a proof.
+//   DIV_MARKSTEIN1: one correction step.  Also equal to RN(n/d): the error of the value before
+//                   the last rounding can only cross a rounding boundary for the finitely many
+//                   significand pairs whose quotient lies within a few 2^-48 of a midpoint, and
+//                   tools/prove_division.c enumerates and checks all of those.
 enum DivMode { DIV_IEEE = 0, DIV_MARKSTEIN2 = 2, DIV_MARKSTEIN1 = 1 };
 
 struct RayCtx {
@@ -214,7 +237,8 @@ __device__ __forceinline__ bool ray_is_tame(const RayCtx& r)
 // extend.cl:40-81.  The traversal order, the tie rules (dist1 > dist2 swaps, so ties keep child
 // 1 first; strict t < dist keeps the first-found triangle) and the distance culling are the
 // reference's.  `pairs` holds, per inner node, its two children's boxes and references
-// (4 x float4); `wtris` holds leaf triangles in leaf order (3 x float4).
+// (4 x float4); `wtris` holds leaf triangles in leaf order (4 x float4:
+// v0+tag, edge1, edge2, pad -- two 32-byte sectors).
 template <int DIV, int STACK>
 __device__ __forceinline__ void bvh_intersect(RayCtx& ray, const float4* __restrict__ pairs,
                                               const float4* __restrict__ wtris, uint32_t rootRef)
@@ -227,21 +251,24 @@ __device__ __forceinline__ void bvh_intersect(RayCtx& ray, const float4* __restr
             uint32_t slot = cur & ~kLeafFlag;
             uint32_t w;
             do {
-                const float4* t = wtris + 3ull * slot;
-                float4 t0 = __ldg(t), e1 = __ldg(t + 1), e2 = __ldg(t + 2);
-                w = __float_as_uint(t0.w);
-                intersect_tri(ray, t0, e1, e2);
+                const float4* t = wtris + 4ull * slot;
+                F8 ta = ldg256(t), tb = ldg256(t + 2);
+                w = __float_as_uint(ta.lo.w);
+                intersect_tri(ray, ta.lo, ta.hi, tb.lo);
                 slot++;
             } while (!(w & kLastFlag));
             if (sp == 0) break;
             cur = stack[--sp];
+            // back to the loop head: leaf lanes and inner-node lanes run as two independent paths
+            // until then, which lets the hardware overlap the triangle loads of the former with
+            // the box tests of the latter (falling through into the inner step measured 13 % slower)
             continue;
         }
         const float4* p = pairs + 4ull * cur;
-        float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
-        float d1 = intersect_aabb<DIV>(ray, q0, q1);
-        float d2 = intersect_aabb<DIV>(ray, q2, q3);
-        uint32_t c1 = __float_as_uint(q0.w), c2 = __float_as_uint(q2.w);
+        F8 ca = ldg256(p), cb = ldg256(p + 2);
+        float d1 = intersect_aabb<DIV>(ray, ca.lo, ca.hi);
+        float d2 = intersect_aabb<DIV>(ray, cb.lo, cb.hi);
+        uint32_t c1 = __float_as_uint(ca.lo.w), c2 = __float_as_uint(cb.lo.w);
         if (d1 > d2) {
             float d = d1; d1 = d2; d2 = d;
             uint32_t c = c1; c1 = c2; c2 = c;
@@ -276,7 +303,8 @@ __device__ __forceinline__ void trace_one(RayCtx& ray, const float4* __restrict_
 
 __device__ __forceinline__ void load_ray(const float4* __restrict__ rays, long long i, RayCtx& ray)
 {
-    float4 a = rays[2 * i], b = rays[2 * i + 1];
+    F8 r = ld256(rays + 2 * i);
+    float4 a = r.lo, b = r.hi;
     ray.dx = a.x; ray.dy = a.y; ray.dz = a.z;
     ray.ox = a.w; ray.oy = b.x; ray.oz = b.y;
     ray.dist = b.z;
@@ -291,14 +319,103 @@ __device__ __forceinline__ void store_hit(float4* __restrict__ rays, long long i
     *p = make_float2(ray.dist, __uint_as_float(ray.tri));
 }
 
+// ---- ray binning (queue re-ordering between generate and extend) --------------------------------
+// Rays of one launch leave the lamp in random directions; a warp of 32 consecutive rays walks 32
+// unrelated paths through the tree.  Before extend, rays are therefore ordered by a coarse key --
+// (origin slice along the lamp, dir.y cell, azimuth cell); the cells are equal-probability for the
+// lamp's uniform emission -- with a counting sort: k_bin_count takes a slot in the ray's bin
+// (one atomic per ray on a 2^16-entry table, so almost never contended), k_bin_scan turns counts
+// into offsets, k_bin_scatter writes the permutation.  Extend then visits rays through the
+// permutation and writes results back to the ray's own slot, so the ray buffer keeps the
+// reference's order and every per-ray result is unchanged.
+struct BinDims { int nY, nT, nP; float y0, invLen; };
+
+__device__ __forceinline__ uint32_t bin_key(const BinDims& d, float dx, float dy, float dz, float oy)
+{
+    int t = min(d.nT - 1, max(0, (int)((dy + 1.0f) * 0.5f * (float)d.nT)));
+    int ph = min(d.nP - 1, max(0, (int)((atan2f(dz, dx) + 3.14159265f) * 0.159154943f * (float)d.nP)));
+    int y = min(d.nY - 1, max(0, (int)((oy - d.y0) * d.invLen * (float)d.nY)));
+    return (uint32_t)((y * d.nT + t) * d.nP + ph);
+}
+
+__global__ void __launch_bounds__(256) k_bin_count(const float4* __restrict__ rays, uint32_t nRays, BinDims d,
+                                                   unsigned int* __restrict__ binCount, uint2* __restrict__ keyRank)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nRays) return;
+    F8 r = ld256(rays + 2ull * i);
+    uint32_t key = bin_key(d, r.lo.x, r.lo.y, r.lo.z, r.hi.x);
+    uint32_t rank = atomicAdd(&binCount[key], 1u);
+    keyRank[i] = make_uint2(key, rank);
+}
+
+// exclusive scan of nBins counters (nBins a multiple of 4096) by one block; also clears the
+// counters for the next launch.  Each thread owns nBins/1024 consecutive counters and moves them
+// as 16-byte vectors with all loads issued before the first use, so the whole scan costs a couple
+// of memory round trips instead of one per counter.
+template <int VEC>   // uint4 vectors per thread
+__global__ void __launch_bounds__(1024) k_bin_scan(uint4* __restrict__ binCount, uint4* __restrict__ binStart)
+{
+    __shared__ unsigned int warpSums[32];
+    uint4 c[VEC];
+    const int base4 = threadIdx.x * VEC;
+#pragma unroll
+    for (int k = 0; k < VEC; k++) c[k] = binCount[base4 + k];
+    unsigned int local = 0;
+#pragma unroll
+    for (int k = 0; k < VEC; k++) local += c[k].x + c[k].y + c[k].z + c[k].w;
+    unsigned int v = local;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (unsigned)o) v += n;
+    }
+    if (lane == 31) warpSums[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        unsigned int s = warpSums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int n = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= (unsigned)o) s += n;
+        }
+        warpSums[lane] = s;
+    }
+    __syncthreads();
+    unsigned int run = (v - local) + (w ? warpSums[w - 1] : 0u);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < VEC; k++) {
+        uint4 o;
+        o.x = run; run += c[k].x;
+        o.y = run; run += c[k].y;
+        o.z = run; run += c[k].z;
+        o.w = run; run += c[k].w;
+        binStart[base4 + k] = o;
+        binCount[base4 + k] = zero;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bin_scatter(const uint2* __restrict__ keyRank, const unsigned int* __restrict__ binStart,
+                                                     uint32_t nRays, uint32_t* __restrict__ perm)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nRays) return;
+    uint2 kr = keyRank[i];
+    perm[binStart[kr.x] + kr.y] = i;
+}
+
 // Variant A: one thread per ray, the literal control flow of extend.cl:85-99.
-template <int DIV, int STACK>
-__global__ void __launch_bounds__(128) k_extend_simple(int* __restrict__ counts, const float4* __restrict__ wtris,
+template <int DIV, int STACK, int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) k_extend_simple(int* __restrict__ counts, const float4* __restrict__ wtris,
                                                        float4* __restrict__ rays, const float4* __restrict__ pairs,
-                                                       uint32_t rootRef, long long nRays, int sceneTame)
+                                                       uint32_t rootRef, long long nRays, int sceneTame,
+                                                       const uint32_t* __restrict__ perm)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nRays) return;
+    if (perm) i = perm[i];
     RayCtx ray;
     load_ray(rays, i, ray);
     trace_one<DIV, STACK>(ray, pairs, wtris, rootRef, sceneTame != 0);
@@ -332,7 +449,7 @@ template <int DIV, int STACK, int K, int REFILL, int HIST, int THREADS, int MINB
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 k_extend_persist(int* __restrict__ counts, const float4* __restrict__ wtris, float4* __restrict__ rays,
                  const float4* __restrict__ pairs, uint32_t rootRef, uint32_t nRays, int sceneTame,
-                 unsigned int* __restrict__ queueHead)
+                 unsigned int* __restrict__ queueHead, const uint32_t* __restrict__ perm)
 {
     constexpr int HBITS = 11;
     __shared__ HitTable<HIST ? HBITS : 1> tab;
@@ -361,8 +478,8 @@ k_extend_persist(int* __restrict__ counts, const float4* __restrict__ wtris, flo
             if (!busy) {
                 unsigned idx = base + __popc(idle & ((1u << lane) - 1u));
                 if (base < nRays && idx < nRays) {
-                    rayIdx = idx;
-                    load_ray(rays, idx, ray);
+                    rayIdx = perm ? perm[idx] : idx;
+                    load_ray(rays, rayIdx, ray);
                     tame = false;
                     if (DIV != DIV_IEEE && sceneTame && ray_is_tame(ray)) {
                         tame = true;
@@ -382,16 +499,16 @@ k_extend_persist(int* __restrict__ counts, const float4* __restrict__ wtris, flo
 #pragma unroll 1
             for (int k = 0; k < K && busy && !(cur & kLeafFlag); k++) {
                 const float4* p = pairs + 4ull * cur;
-                float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+                F8 ca = ldg256(p), cb = ldg256(p + 2);
                 float d1, d2;
                 if (DIV == DIV_IEEE || !tame) {
-                    d1 = intersect_aabb<DIV_IEEE>(ray, q0, q1);
-                    d2 = intersect_aabb<DIV_IEEE>(ray, q2, q3);
+                    d1 = intersect_aabb<DIV_IEEE>(ray, ca.lo, ca.hi);
+                    d2 = intersect_aabb<DIV_IEEE>(ray, cb.lo, cb.hi);
                 } else {
-                    d1 = intersect_aabb<DIV>(ray, q0, q1);
-                    d2 = intersect_aabb<DIV>(ray, q2, q3);
+                    d1 = intersect_aabb<DIV>(ray, ca.lo, ca.hi);
+                    d2 = intersect_aabb<DIV>(ray, cb.lo, cb.hi);
                 }
-                uint32_t c1 = __float_as_uint(q0.w), c2 = __float_as_uint(q2.w);
+                uint32_t c1 = __float_as_uint(ca.lo.w), c2 = __float_as_uint(cb.lo.w);
                 if (d1 > d2) {
                     float d = d1; d1 = d2; d2 = d;
                     uint32_t c = c1; c1 = c2; c2 = c;
@@ -407,10 +524,10 @@ k_extend_persist(int* __restrict__ counts, const float4* __restrict__ wtris, flo
                 uint32_t slot = cur & ~kLeafFlag;
                 uint32_t w;
                 do {
-                    const float4* t = wtris + 3ull * slot;
-                    float4 t0 = __ldg(t), e1 = __ldg(t + 1), e2 = __ldg(t + 2);
-                    w = __float_as_uint(t0.w);
-                    intersect_tri(ray, t0, e1, e2);
+                    const float4* t = wtris + 4ull * slot;
+                    F8 ta = ldg256(t), tb = ldg256(t + 2);
+                    w = __float_as_uint(ta.lo.w);
+                    intersect_tri(ray, ta.lo, ta.hi, tb.lo);
                     slot++;
                 } while (!(w & kLastFlag));
                 if (sp == 0) busy = false; else cur = stack[--sp];

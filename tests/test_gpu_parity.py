@@ -1,0 +1,376 @@
+"""Parity of the CUDA path (through the C ABI of include/uvrt.h / uvrt_host.h) against the oracle
+on identical inputs.  Everything here needs a B200: run with `-m gpu`.
+
+Bars: generate 32-byte records bit-equal; extend (dist bits, triID)
+equal for EVERY ray and per-triangle counts integer-equal; accumulate / computeDosage /
+dosageToColor / reset bit-equal (stricter than the 1-ulp allowance); end-to-end dose within
+rel. 1e-3 (north_star) -- and in fact bit-equal, which is asserted too."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import uvrt_testlib as T
+from conftest import lange_pos0
+
+pytestmark = pytest.mark.gpu
+
+DOSE_RTOL = 1e-3          # tolerance stated by BASELINE.json north_star
+SIMPLE_VARIANTS = [0, 1, 2]
+PERSIST_VARIANTS = [10, 11, 12, 16, 17, 19, 20, 22, 23, 24]
+
+
+@pytest.fixture(scope="module")
+def ctx(uv, room):
+    c = uv.Context(0)
+    tris, nodes, tri_idx, _ = room
+    c.upload_scene(tris, nodes, tri_idx)
+    yield c
+    c.close()
+
+
+def oracle_launch(room, lp, P, seed_in=0, first=0, light_length=1.0):
+    tris, nodes, tri_idx, _ = room
+    O = T.oracle()
+    rays = np.zeros(P, dtype=T.RAY_DT)
+    so = C.c_uint32(0)
+    O.orc_generate(T.ptr(rays), first, P, lp[0], lp[1], lp[2], light_length, seed_in, C.byref(so))
+    gen = rays.copy()
+    temp = np.zeros(tris.shape[0], dtype=np.int32)
+    cnt = T.Counters()
+    O.orc_extend(T.ptr(temp), T.ptr(tris), T.ptr(rays), T.ptr(nodes), T.ptr(tri_idx), P, 0, C.byref(cnt))
+    return gen, rays, temp, int(so.value), cnt
+
+
+def test_device_is_blackwell(uv, ctx):
+    info = ctx.device_info()
+    assert info["cc"][0] >= 10, info
+    s = ctx.scene_info()
+    assert s["inner"] + s["leaves"] == 89417 and s["leaves"] == 44709 and s["depth"] == 21
+
+
+def test_generate_bit_exact_and_golden(uv, ctx, room, golden):
+    lp = lange_pos0(room[3])
+    P = 1000000
+    ctx.generate(lp, 1.0, 0, P, 0)
+    got = ctx.read(uv.BUF.RAYS, P)
+    want, _, _, seed_out, _ = oracle_launch(room, lp, P)
+    assert got.tobytes() == want.tobytes()
+    assert f"{T.fnv(got):016x}" == golden["launch"][str(P)]["fnv_rays_after_generate"]
+    chain = ctx.seed_chain([lp], 1.0, 0)
+    assert int(chain[1]) == seed_out == golden["launch"][str(P)]["seed_out"]
+
+
+@pytest.mark.parametrize("first,seed_in,length", [(0, 0xdeadbeef, 1.0), (5_000_001, 435838349, 0.37), (126_000_000, 1, 2.5)])
+def test_generate_shards_reproduce_global_ids(uv, ctx, room, first, seed_in, length):
+    lp = (np.float32(0.51000142), np.float32(-0.7), np.float32(-0.25500044))
+    P = 300_001
+    ctx.generate(lp, length, first, P, seed_in)
+    got = ctx.read(uv.BUF.RAYS, P)
+    want = oracle_launch(room, lp, P, seed_in, first, length)[0]
+    assert got.tobytes() == want.tobytes()
+
+
+def test_seed_chain_matches_golden(uv, ctx, room, golden):
+    g = golden["pass_lange_route"]
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_route("lange_route")
+    pos, p = sim.positions, sim.params
+    f32 = np.float32
+    lps = [(f32(x), f32(f32(room[3]) + f32(p.lightHeight)), f32(y)) for x, y, _ in pos]
+    chain = ctx.seed_chain(lps, p.lightLength, 0)
+    assert [int(s) for s in chain] == g["seed_chain"]
+
+
+@pytest.mark.parametrize("variant", SIMPLE_VARIANTS + PERSIST_VARIANTS)
+@pytest.mark.parametrize("hist,binned", [(0, 1), (1, 1), (0, 0)])
+def test_extend_bit_exact(uv, ctx, room, golden, variant, hist, binned):
+    if hist and variant < 10:
+        pytest.skip("hist_mode only exists for the persistent kernels")
+    lp = lange_pos0(room[3])
+    P = 1000000
+    gen, want, want_counts, _, _ = oracle_launch(room, lp, P)
+    ctx.set_option("extend_variant", variant)
+    ctx.set_option("hist_mode", hist)
+    ctx.set_option("bin_rays", binned)
+    try:
+        ctx.reset(True)
+        ctx.write(uv.BUF.RAYS, gen)
+        ctx.extend(P)
+        got = ctx.read(uv.BUF.RAYS, P)
+        counts = ctx.read(uv.BUF.COUNTS)
+    finally:
+        ctx.set_option("extend_variant", -1)
+        ctx.set_option("hist_mode", 0)
+        ctx.set_option("bin_rays", 1)
+    bad = np.flatnonzero((got["dist"].view(np.uint32) != want["dist"].view(np.uint32)) | (got["triID"] != want["triID"]))
+    assert bad.size == 0, f"{bad.size} rays differ, first {bad[:5]}: {got[bad[:3]]} vs {want[bad[:3]]}"
+    assert got.tobytes() == want.tobytes()
+    assert np.array_equal(counts, want_counts)
+    g = golden["launch"][str(P)]
+    assert f"{T.fnv(counts):016x}" == g["fnv_counts"]
+    assert f"{int(T.oracle().orc_fnv_hits(T.ptr(got), P)):016x}" == g["fnv_hits"]
+
+
+def test_full_size_launch_matches_golden(uv, ctx, room, golden):
+    """The launch size of the default route: 2,796,202 rays, default kernel, fused trace call."""
+    lp = lange_pos0(room[3])
+    P = 2796202
+    g = golden["launch"][str(P)]
+    ctx.reset(True)
+    ctx.trace_counts(lp, 1.0, 0, P, 0)
+    rays = ctx.read(uv.BUF.RAYS, P)
+    counts = ctx.read(uv.BUF.COUNTS)
+    assert f"{int(T.oracle().orc_fnv_hits(T.ptr(rays), P)):016x}" == g["fnv_hits"]
+    assert f"{T.fnv(counts):016x}" == g["fnv_counts"]
+    assert int(counts.sum()) == g["hits"] == int((rays["dist"] != np.float32(1e30)).sum())
+    assert [int(counts.argmax()), int(counts.max())] == g["hottest"]
+    for i, hexs in g["samples"].items():
+        assert rays[int(i)].tobytes().hex() == hexs
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 11, 23])
+@pytest.mark.parametrize("binned", [0, 1])
+def test_extend_degenerate_rays(uv, ctx, room, variant, binned):
+    """Axis-parallel directions (division by zero, 0/0 = NaN on slab planes), origins outside the
+    room, zero-length directions: the strict path must reproduce the oracle's IEEE behaviour."""
+    tris, nodes, tri_idx, floor = room
+    rng = np.random.default_rng(5)
+    n = 70000 if binned else 20000      # binning starts at 65,536 rays
+    rays = np.zeros(n, dtype=T.RAY_DT)
+    rays["orig"] = rng.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:6000, 0] = 0.0                                # one exact zero
+    d[2000:8000, 2] = 0.0                            # two exact zeros for 2000..5999
+    d[8000:8100] = 0.0                               # null directions
+    d[8050:8100, 1] = np.nan                          # NaN directions
+    d[8100:8200] *= 1e-20                            # tiny directions (not 'tame')
+    rays["dir"] = d.astype(np.float32)
+    boxmin = nodes[0]["min"]
+    rays["orig"][:3000, 0] = boxmin[0]               # on a slab plane with dir.x == 0 -> 0/0
+    rays["orig"][9000:9500] = 0.0                    # exact zero origin
+    rays["orig"][9500:10000] *= 1e-9                 # tiny origin (not 'tame')
+    rays["orig"][10000:10500] += 50.0                # outside the room
+    rays["dist"] = 1e30
+    want = rays.copy()
+    wc = np.zeros(tris.shape[0], dtype=np.int32)
+    T.oracle().orc_extend(T.ptr(wc), T.ptr(tris), T.ptr(want), T.ptr(nodes), T.ptr(tri_idx), n, 0, None)
+    ctx.set_option("extend_variant", variant)
+    ctx.set_option("bin_rays", binned)
+    try:
+        ctx.reset(True)
+        ctx.write(uv.BUF.RAYS, rays)
+        ctx.extend(n)
+        got = ctx.read(uv.BUF.RAYS, n)
+        counts = ctx.read(uv.BUF.COUNTS)
+    finally:
+        ctx.set_option("extend_variant", -1)
+        ctx.set_option("bin_rays", 1)
+    assert got.tobytes() == want.tobytes()
+    assert np.array_equal(counts, wc)
+
+
+def test_per_triangle_passes_bit_exact(uv, ctx, room):
+    tris = room[0]
+    n = tris.shape[0]
+    O = T.oracle()
+    rng = np.random.default_rng(9)
+    pm, mx = np.zeros(n), np.zeros(n)
+    ctx.reset(True)
+    for dur in (60.0, 0.1, 7.25):
+        temp = rng.integers(0, 70000, n).astype(np.int32)
+        temp[::5] = 0
+        ctx.write(uv.BUF.COUNTS, temp)
+        ctx.accumulate(dur)
+        O.orc_accumulate(T.ptr(pm), T.ptr(mx), T.ptr(temp), np.float32(dur), n)
+        assert not ctx.read(uv.BUF.COUNTS).any()
+    assert ctx.read(uv.BUF.SUM).tobytes() == pm.tobytes()
+    assert ctx.read(uv.BUF.MAX).tobytes() == mx.tobytes()
+    for use_max, ppl, power, minv, thr in ((0, 2796202, 44.019705, 100.0, 0), (1, 2796202, 44019.705, 1500.0, 1), (0, 1, 1.0, 1e-3, 1)):
+        ctx.shade(use_max, ppl, power)
+        ctx.color(minv, thr)
+        dose = np.zeros(n, dtype=np.float32)
+        O.orc_compute_dosage(T.ptr(mx if use_max else pm), T.ptr(dose), T.ptr(tris), ppl, np.float32(power), n)
+        col = np.zeros((n, 9), dtype=np.float32)
+        O.orc_dosage_to_color(T.ptr(dose), T.ptr(col), np.float32(minv), thr, n)
+        assert ctx.read(uv.BUF.DOSE).tobytes() == dose.tobytes()
+        assert ctx.read(uv.BUF.COLOR).tobytes() == col.tobytes()
+    ctx.reset(False)
+    assert not ctx.read(uv.BUF.SUM).any() and not ctx.read(uv.BUF.MAX).any()
+    assert ctx.read(uv.BUF.COLOR).any()
+    ctx.reset(True)
+    assert not ctx.read(uv.BUF.COLOR).any()
+
+
+def oracle_route_run(room, pos, p, iterations, photons_per_light, seed=0):
+    tris, nodes, tri_idx, floor = room
+    O = T.oracle()
+    n = tris.shape[0]
+    f32 = np.float32
+    pm, mx, temp = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32)
+    rays = np.zeros(photons_per_light, dtype=T.RAY_DT)
+    total = 0
+    for _ in range(iterations):
+        for (x, y, dur) in pos:
+            so = C.c_uint32(0)
+            O.orc_generate(T.ptr(rays), 0, photons_per_light, f32(x), f32(f32(floor) + f32(p.lightHeight)), f32(y),
+                           f32(p.lightLength), seed, C.byref(so))
+            O.orc_extend(T.ptr(temp), T.ptr(tris), T.ptr(rays), T.ptr(nodes), T.ptr(tri_idx), photons_per_light, 0, None)
+            O.orc_accumulate(T.ptr(pm), T.ptr(mx), T.ptr(temp), f32(dur), n)
+            seed = int(so.value)
+            total += photons_per_light
+    dose = np.zeros(n, dtype=np.float32)
+    O.orc_compute_dosage(T.ptr(pm), T.ptr(dose), T.ptr(tris), total // len(pos), f32(f32(p.lightIntensity) * f32(0.1)), n)
+    col = np.zeros((n, 9), dtype=np.float32)
+    O.orc_dosage_to_color(T.ptr(dose), T.ptr(col), f32(p.minDosage), 0, n)
+    return pm, mx, dose, col, seed
+
+
+@pytest.mark.parametrize("route", ["route", "lange_route"])
+def test_raytracer_end_to_end(uv, room, route):
+    """The drop-in RayTracer (LoadMesh -> Init -> ResetDosageMap -> Tick loop) against the oracle."""
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_mesh("testroomopt")
+    sim.init(route)
+    sim.set_params(photonCount=1 << 22, maxIterations=2)
+    p = sim.params
+    assert p.photonsPerLight == ((1 << 22) // 12) & ~1
+    dose = sim.run()
+    c = sim.ctx
+    pm, mx, want, col, seed = oracle_route_run(room, sim.positions, p, 2, p.photonsPerLight)
+    nz = want != 0
+    assert np.array_equal(nz, dose != 0)
+    rel = np.abs(dose[nz].astype(np.float64) - want[nz]) / want[nz]
+    assert rel.max() <= DOSE_RTOL
+    assert dose.tobytes() == want.tobytes()          # in fact bit-identical
+    assert c.read(uv.BUF.SUM).tobytes() == pm.tobytes()
+    assert c.read(uv.BUF.MAX).tobytes() == mx.tobytes()
+    assert c.read(uv.BUF.COLOR).tobytes() == col.tobytes()
+    q = sim.params
+    assert q.seedState == seed and q.currIterations == 2 and q.finishedComputation
+    assert q.photonMapSize == 2 * 12 * p.photonsPerLight == sim.rays_traced()
+    sim.close()
+
+
+def test_full_pass_matches_golden(uv, room, golden):
+    """One pass over lange_route at the default size (12 x 2,796,202 rays) against the vectors
+    produced by the reference's own compiled sources (App. C.2)."""
+    g = golden["pass_lange_route"]
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_mesh("testroomopt")
+    sim.init("lange_route")
+    sim.set_params(maxIterations=1)
+    dose = sim.run()
+    c = sim.ctx
+    assert f"{T.fnv(c.read(uv.BUF.SUM)):016x}" == g["fnv_photonMap"]
+    assert f"{T.fnv(c.read(uv.BUF.MAX)):016x}" == g["fnv_maxPhotonMap"]
+    assert f"{T.fnv(dose):016x}" == g["fnv_dose"]
+    assert f"{T.fnv(c.read(uv.BUF.COLOR)):016x}" == g["fnv_color"]
+    assert [int(v) for v in dose[:8].view(np.uint32)] == g["dose_head_bits"]
+    assert int((dose == 0).sum()) == g["unlit"]
+    assert sim.params.seedState == g["seed_chain"][-1]
+    # energy bookkeeping at full size: every hit landed in exactly one triangle's sum
+    assert int(round(c.read(uv.BUF.SUM).sum() / 60.0)) == sum(g["hits_per_position"])
+    sim.close()
+
+
+def test_sharded_run_equals_single(uv, room):
+    """Launches dealt round-robin to two 'ranks' (here: two contexts on one GPU, combined on the
+    host the way uvrt_reduce combines them) reproduce the single-context maps exactly."""
+    results = []
+    for rank, count in ((0, 1), (0, 2), (1, 2)):
+        sim = uv.Sim(asset_root=T.DATA)
+        sim.load_mesh("testroomopt")
+        sim.init("route")
+        sim.set_params(photonCount=1 << 21, maxIterations=3)
+        sim.set_shard(rank, count)
+        sim.reset_dosage_map()
+        while not sim.tick():
+            pass
+        c = sim.ctx
+        results.append((c.read(uv.BUF.SUM), c.read(uv.BUF.MAX), sim.params.seedState, sim.params.photonMapSize, sim.rays_traced()))
+        sim.close()
+    one, a, b = results
+    assert np.array_equal(one[0], a[0] + b[0])
+    assert np.array_equal(one[1], np.maximum(a[1], b[1]))
+    assert one[2] == a[2] == b[2] and one[3] == a[3] == b[3]
+    assert one[4] == a[4] + b[4]
+
+
+def test_split_launch_counts_add_up(uv, ctx, room):
+    """A launch cut into ray ranges (firstRay) gives the same counts as the whole launch."""
+    lp = lange_pos0(room[3])
+    P = 500_000
+    ctx.reset(True)
+    ctx.trace_counts(lp, 1.0, 0, P, 77)
+    whole = ctx.read(uv.BUF.COUNTS)
+    ctx.reset(True)
+    parts = np.zeros_like(whole)
+    for first, n in ((0, 123_457), (123_457, 0), (123_457, 300_000), (423_457, 76_543)):
+        ctx.trace_counts(lp, 1.0, first, n, 77)
+    parts = ctx.read(uv.BUF.COUNTS)
+    assert np.array_equal(whole, parts)
+
+
+def test_calibration_scene_and_analytic_irradiance(uv, room):
+    """CalibratePower (raytracer.cpp:151-227): a 2-triangle scene whose BVH root is a leaf.  With
+    power 1 the simulated irradiance on the patch must match the closed form for a uniformly
+    radiating line source, E = 1/(4 pi L d) * [s / sqrt(d^2 + s^2)] over the lamp's extent."""
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_mesh("testroomopt")
+    sim.init("route")
+    sim.set_params(photonCount=1 << 23, maxIterations=2)
+    p = sim.params
+    d, h, L, lh = 1.0, 1.0, p.lightLength, p.lightHeight
+    measured = 123.0
+    calibrated = sim.calibrate(measured, h, d)
+    # lamp spans [lh, lh + L] above the floor; patch centre at height h, distance d
+    s0, s1 = lh - h, lh + L - h
+    E = (s1 / np.hypot(d, s1) - s0 / np.hypot(d, s0)) / (4 * np.pi * L * d)
+    expect = 0.01 * measured / E
+    assert abs(calibrated - expect) / expect < 0.03          # Monte-Carlo error of ~2e4 hits + finite patch
+    assert sim.params.lightIntensity == np.float32(calibrated)
+    # the room is back: a normal run still matches the oracle
+    sim.set_params(photonCount=1 << 20, maxIterations=1, lightIntensity=443.31842)
+    seed0 = sim.params.seedState
+    dose = sim.run()
+    want = oracle_route_run(room, sim.positions, sim.params, 1, sim.params.photonsPerLight, seed0)[2]
+    assert dose.tobytes() == want.tobytes()
+    sim.close()
+
+
+def test_shared_reciprocal_division_equals_ieee(ctx):
+    samples, bad1, bad2 = ctx.selftest_division(blocks=148 * 16, iters=8192)
+    assert samples == 148 * 16 * 256 * 8192
+    assert bad2 == 0, "two-step Markstein quotient differs from __fdiv_rn"
+    assert bad1 == 0, "one-step Markstein quotient differs from __fdiv_rn"
+
+
+def test_error_codes_instead_of_aborts(uv, room):
+    tris, nodes, tri_idx, _ = room
+    c = uv.Context(0)
+    with pytest.raises(uv.UvrtError) as e:
+        c.extend(10)
+    assert e.value.code == -3                                  # no scene yet
+    with pytest.raises(uv.UvrtError) as e:
+        c.upload_scene(tris, nodes[: 2 * tris.shape[0]], tri_idx)   # the reference's truncated upload (App. B-3)
+    assert e.value.code == -1 and "reachable" in str(e.value)
+    bad_idx = tri_idx.copy()
+    bad_idx[10] = 10**9
+    with pytest.raises(uv.UvrtError):
+        c.upload_scene(tris, nodes, bad_idx)
+    loop = nodes.copy()
+    loop[2]["leftFirst"] = 0                                    # a cycle
+    with pytest.raises(uv.UvrtError):
+        c.upload_scene(tris, loop, tri_idx)
+    c.upload_scene(tris, nodes, tri_idx)                        # still usable
+    c.generate((0, 0, 0), 1.0, 0, 0, 0)                         # zero rays: a no-op
+    c.extend(0)
+    with pytest.raises(uv.UvrtError):
+        c.extend(1 << 40)
+    with pytest.raises(uv.UvrtError):
+        c.set_option("no_such_option", 1)
+    with pytest.raises(uv.UvrtError):
+        uv.Context(99)
+    c.close()

@@ -171,3 +171,20 @@ def test_route_missing_or_broken_file_keeps_settings(uv, tmp_path):
     assert sim.positions.tolist() == [[1.5, -2.0, 3.0]]
     assert sim.params.photonsPerLight == 1000
     uv.Sim(asset_root=T.DATA)
+
+
+def test_shared_reciprocal_division_is_proven_exact(tmp_path):
+    """tools/prove_division.c enumerates every significand pair whose quotient lies within 8
+    numerator units of a rounding boundary (the only inputs for which the one-step quotient of the
+    extend kernel could misround) and checks them, plus random pairs, against the CPU's
+    correctly rounded division."""
+    import subprocess
+    exe = str(tmp_path / "prove_division")
+    src = os.path.join(T.ROOT, "tools", "prove_division.c")
+    r = subprocess.run(["gcc", "-O2", "-mfma", "-fopenmp", "-ffp-contract=off", "-o", exe, src, "-lm"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cannot build with -mfma here: " + r.stderr[-200:])
+    r = subprocess.run([exe, "26"], capture_output=True, text=True, timeout=600)
+    assert "FAILURES 0" in r.stdout and r.returncode == 0, r.stdout[-500:]
+    assert "hard cases (|num| <= 8) 46517418" in r.stdout
