@@ -160,8 +160,8 @@ def traversal_stats(room, positions, params, sample_per_launch=200_000):
     return cnt.innerVisits / rays, cnt.triTests / rays
 
 
-def load_room_host(uv):
-    sim = uv.Sim(asset_root=DATA)
+def load_room_host(uv, device=0):
+    sim = uv.Sim(asset_root=DATA, device=device)
     sim.load_mesh(ROOM)
     sim.load_route(ROUTE)
     tris, nodes, tri_idx = sim.mesh_data()
@@ -232,7 +232,7 @@ def main():
 
     uv = importlib.import_module("small-project-uv-robot-ray-tracer_b200")
     B = importlib.import_module("small-project-uv-robot-ray-tracer_b200.binding")
-    sim, room = load_room_host(uv)
+    sim, room = load_room_host(uv, local)
     sim.init(ROUTE)                      # fails loudly without a CUDA device
     ctx = sim.ctx
     if args.variant >= 0:
