@@ -109,11 +109,13 @@ struct uvrt_ctx {
     // ray binning (counting sort by direction / origin cell)
     unsigned int* dBinCount = nullptr;
     unsigned int* dBinStart = nullptr;
-    int binCap = 0;
+    unsigned int* dBinBlock = nullptr;   // totals of the scan blocks
+    int binCap = 0, binUsed = 0;
+    long long countedRays = -1;          // rays whose bin slots k_generate already took (-1: none)
     uint2* dKeyRank = nullptr;
     uint32_t* dPerm = nullptr;
     long long permCap = 0;
-    int binRays = 1, binY = 8, binT = 32, binP = 64;
+    int binRays = 1, binY = 16, binT = 32, binP = 128;   // 65,536 bins: best of the sweeps
     float binY0 = 0.0f, binLen = 1.0f;   // lamp extent of the rays in the buffer
     bool binExtentKnown = false;
     int64_t uploadBytes = 0;
@@ -254,6 +256,7 @@ inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block 
 //   2  simple / Markstein one-step
 //   10 + 3*k + d  persistent, K = {1, 2, 4, 8, inf}[k], d = {IEEE, M2, M1}
 constexpr int kStack = 64;
+constexpr long long kMinRaysForBinning = 65536;
 constexpr int kDefaultVariant = 2;   // one thread per ray, one-step shared-reciprocal division (proven exact)
 
 template <int DIV, int THREADS, int MINB>
@@ -269,10 +272,7 @@ void launch_simple(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     // "simple_cfg": block size / resident-blocks hint (register cap) of the one-thread-per-ray kernel
     switch (ctx->simpleCfg) {
     case 1: launch_simple_cfg<DIV, 128, 12>(ctx, nRays, perm); break;   // <= 40 registers: 48 warps/SM
-    case 2: launch_simple_cfg<DIV, 128, 16>(ctx, nRays, perm); break;   // <= 32 registers: 64 warps/SM
-    case 3: launch_simple_cfg<DIV, 64, 20>(ctx, nRays, perm); break;
-    case 4: launch_simple_cfg<DIV, 256, 5>(ctx, nRays, perm); break;
-    case 5: launch_simple_cfg<DIV, 32, 32>(ctx, nRays, perm); break;
+    case 3: launch_simple_cfg<DIV, 64, 24>(ctx, nRays, perm); break;    // <= 40 registers, smaller blocks
     default: launch_simple_cfg<DIV, 128, 1>(ctx, nRays, perm); break;
     }
 }
@@ -319,25 +319,29 @@ void launch_persist_d(uvrt_ctx* ctx, long long nRays, int d, const uint32_t* per
     else launch_persist_h<DIV_MARKSTEIN1, K>(ctx, nRays, perm);
 }
 
-// Counting sort of the ray queue by (origin slice, dir.y cell, azimuth cell); fills ctx->dPerm.
-int bin_rays(uvrt_ctx* ctx, long long nRays)
+// Counting sort of the ray queue (kernels: uvrt_kernels.cuh "ray binning").  bin_prepare sizes the
+// tables; the count step runs inside k_generate (countedRays) or as k_bin_count; bin_finish scans and
+// scatters, leaving the permutation in ctx->dPerm.
+int bin_prepare(uvrt_ctx* ctx, long long nRays, BinDims* d)
 {
-    // the scan kernel handles 4096 * VEC counters; the table is padded up to the next supported size
     const int wanted = ctx->binY * ctx->binT * ctx->binP;
-    int nBins = 4096;
+    int nBins = kBinsPerScanBlock;
     while (nBins < wanted) nBins *= 2;
-    if (nBins > (4096 << 4))
-        return fail(ctx, UVRT_ERR_INVALID, "bin_y*bin_t*bin_p = %d exceeds the supported %d bins", wanted, 4096 << 4);
+    if (nBins > 64 * kBinsPerScanBlock)
+        return fail(ctx, UVRT_ERR_INVALID, "bin_y*bin_t*bin_p = %d exceeds the supported %d bins", wanted, 64 * kBinsPerScanBlock);
     if (nBins > ctx->binCap) {
         if (ctx->dBinCount) cudaFree(ctx->dBinCount);
         if (ctx->dBinStart) cudaFree(ctx->dBinStart);
-        ctx->dBinCount = ctx->dBinStart = nullptr;
+        if (ctx->dBinBlock) cudaFree(ctx->dBinBlock);
+        ctx->dBinCount = ctx->dBinStart = ctx->dBinBlock = nullptr;
         ctx->binCap = 0;
         CK(cudaMalloc((void**)&ctx->dBinCount, (size_t)nBins * 4));
         CK(cudaMalloc((void**)&ctx->dBinStart, (size_t)nBins * 4));
+        CK(cudaMalloc((void**)&ctx->dBinBlock, 64 * 4));
         CK(cudaMemsetAsync(ctx->dBinCount, 0, (size_t)nBins * 4, ctx->stream));
         ctx->binCap = nBins;
     }
+    ctx->binUsed = nBins;
     if (nRays > ctx->permCap) {
         if (ctx->dKeyRank) cudaFree(ctx->dKeyRank);
         if (ctx->dPerm) cudaFree(ctx->dPerm);
@@ -346,25 +350,33 @@ int bin_rays(uvrt_ctx* ctx, long long nRays)
         CK(cudaMalloc((void**)&ctx->dPerm, (size_t)ctx->rayCap * 4));
         ctx->permCap = ctx->rayCap;
     }
-    BinDims d;
-    d.nY = ctx->binExtentKnown ? ctx->binY : 1;
-    d.nT = ctx->binT;
-    d.nP = ctx->binP;
-    d.y0 = ctx->binY0;
-    d.invLen = ctx->binLen > 0.0f ? 1.0f / ctx->binLen : 0.0f;
+    d->nY = ctx->binExtentKnown ? ctx->binY : 1;
+    d->nT = ctx->binT;
+    d->nP = ctx->binP;
+    d->y0 = ctx->binY0;
+    d->invLen = ctx->binLen > 0.0f ? 1.0f / ctx->binLen : 0.0f;
+    return UVRT_OK;
+}
+
+int bin_finish(uvrt_ctx* ctx, long long nRays)
+{
     StageTimer t(ctx, UVRT_STAGE_BIN);
-    k_bin_count<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dRays, (uint32_t)nRays, d, ctx->dBinCount, ctx->dKeyRank);
-    uint4* bc = reinterpret_cast<uint4*>(ctx->dBinCount);
-    uint4* bs = reinterpret_cast<uint4*>(ctx->dBinStart);
-    switch (nBins / 4096) {
-    case 1: k_bin_scan<1><<<1, 1024, 0, ctx->stream>>>(bc, bs); break;
-    case 2: k_bin_scan<2><<<1, 1024, 0, ctx->stream>>>(bc, bs); break;
-    case 4: k_bin_scan<4><<<1, 1024, 0, ctx->stream>>>(bc, bs); break;
-    case 8: k_bin_scan<8><<<1, 1024, 0, ctx->stream>>>(bc, bs); break;
-    default: k_bin_scan<16><<<1, 1024, 0, ctx->stream>>>(bc, bs); break;
+    if (ctx->countedRays != nRays) {
+        // the rays in the buffer did not (all) come from k_generate<1>: count them now
+        BinDims d;
+        int rc = bin_prepare(ctx, nRays, &d);
+        if (rc) return rc;
+        if (ctx->countedRays >= 0) CK(cudaMemsetAsync(ctx->dBinCount, 0, (size_t)ctx->binCap * 4, ctx->stream));
+        k_bin_count<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dRays, (uint32_t)nRays, d, ctx->dBinCount, ctx->dKeyRank);
+        ctx->launches++;
     }
-    k_bin_scatter<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dKeyRank, ctx->dBinStart, (uint32_t)nRays, ctx->dPerm);
-    ctx->launches += 3;
+    ctx->countedRays = -1;
+    const int nScanBlocks = ctx->binUsed / kBinsPerScanBlock;
+    k_bin_scan<<<nScanBlocks, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(ctx->dBinCount),
+                                                     reinterpret_cast<uint4*>(ctx->dBinStart), ctx->dBinBlock);
+    k_bin_scatter<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dKeyRank, ctx->dBinStart, ctx->dBinBlock, nScanBlocks,
+                                                                 (uint32_t)nRays, ctx->dPerm);
+    ctx->launches += 2;
     return UVRT_OK;
 }
 
@@ -449,7 +461,7 @@ void uvrt_destroy(uvrt_ctx* ctx)
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     void* ptrs[] = {ctx->dPairs, ctx->dWtris, ctx->dVerts, ctx->dCounts, ctx->dSum, ctx->dMax, ctx->dDose,
                     ctx->dColor, ctx->dRays, ctx->dQueue, ctx->dSeeds, ctx->dSeedPos, ctx->dFlush,
-                    ctx->dBinCount, ctx->dBinStart, ctx->dKeyRank, ctx->dPerm};
+                    ctx->dBinCount, ctx->dBinStart, ctx->dBinBlock, ctx->dKeyRank, ctx->dPerm};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->hStage) cudaFreeHost(ctx->hStage);
     for (auto& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
@@ -560,12 +572,15 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
             float* p = hp + (size_t)id[n] * 16;
             for (int c = 0; c < 2; c++) {
                 const HostNode& ch = nodes[nd.leftFirst + c];
+                // (min.x, min.y) (max.x, max.y) (min.z, max.z) (ref, 0): 64-bit pairs for the packed pipe
                 float* q = p + c * 8;
-                q[0] = ch.mn[0]; q[1] = ch.mn[1]; q[2] = ch.mn[2];
+                q[0] = ch.mn[0]; q[1] = ch.mn[1]; q[2] = ch.mx[0]; q[3] = ch.mx[1];
+                q[4] = ch.mn[2]; q[5] = ch.mx[2];
                 uint32_t ref = child_ref(nd.leftFirst + c);
-                memcpy(&q[3], &ref, 4);
-                q[4] = ch.mx[0]; q[5] = ch.mx[1]; q[6] = ch.mx[2]; q[7] = 0.0f;
-                for (int a = 0; a < 3; a++) tame = tame && coord_tame(ch.mn[a]) && coord_tame(ch.mx[a]);
+                memcpy(&q[6], &ref, 4);
+                q[7] = 0.0f;
+                // the fast box test needs normal-range coordinates and min <= max on every axis
+                for (int a = 0; a < 3; a++) tame = tame && coord_tame(ch.mn[a]) && coord_tame(ch.mx[a]) && ch.mn[a] <= ch.mx[a];
             }
         }
     }
@@ -657,10 +672,20 @@ int uvrt_generate(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength
     ctx->binY0 = ly;
     ctx->binLen = lightLength;
     ctx->binExtentKnown = true;
+    ctx->countedRays = -1;
     if (nRays == 0) return UVRT_OK;
-    {
+    if (ctx->binRays && nRays >= kMinRaysForBinning) {
+        BinDims d;
+        rc = bin_prepare(ctx, nRays, &d);
+        if (rc) return rc;
         StageTimer t(ctx, UVRT_STAGE_GENERATE);
-        k_generate<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dRays, firstRay, nRays, lx, ly, lz, lightLength, seedIn);
+        k_generate<1><<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dRays, firstRay, nRays, lx, ly, lz, lightLength, seedIn,
+                                                                      d, ctx->dBinCount, ctx->dKeyRank);
+        ctx->countedRays = nRays;
+    } else {
+        StageTimer t(ctx, UVRT_STAGE_GENERATE);
+        k_generate<0><<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dRays, firstRay, nRays, lx, ly, lz, lightLength, seedIn,
+                                                                      BinDims{1, 1, 1, 0.0f, 0.0f}, nullptr, nullptr);
     }
     ctx->launches++;
     CK_LAUNCH("generate");
@@ -675,12 +700,16 @@ int uvrt_extend(uvrt_ctx* ctx, int64_t nRays)
     if (nRays == 0) return UVRT_OK;
     int rc;
     const uint32_t* perm = nullptr;
-    // a few thousand rays are not worth three extra launches
-    if (ctx->binRays && nRays >= 65536) {
-        rc = bin_rays(ctx, nRays);
+    // a few thousand rays are not worth the extra launches
+    if (ctx->binRays && nRays >= kMinRaysForBinning) {
+        rc = bin_finish(ctx, nRays);
         if (rc) return rc;
         CK_LAUNCH("bin");
         perm = ctx->dPerm;
+    } else if (ctx->countedRays >= 0) {
+        // binning was switched off between generate and extend: drop the slots generate took
+        CK(cudaMemsetAsync(ctx->dBinCount, 0, (size_t)ctx->binCap * 4, ctx->stream));
+        ctx->countedRays = -1;
     }
     {
         StageTimer t(ctx, UVRT_STAGE_EXTEND);
@@ -791,6 +820,10 @@ int uvrt_write(uvrt_ctx* ctx, uvrt_buffer what, const void* src, size_t bytes)
         if (rc) return rc;
         ctx->lastRays = (long long)(bytes / 32);
         ctx->binExtentKnown = false;   // foreign rays: no origin slicing
+        if (ctx->countedRays >= 0 && ctx->dBinCount) {
+            CK(cudaMemsetAsync(ctx->dBinCount, 0, (size_t)ctx->binCap * 4, ctx->stream));
+            ctx->countedRays = -1;
+        }
     }
     void* p = nullptr;
     size_t cap = 0;
@@ -871,10 +904,19 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
     else if (!strcmp(key, "blocks_per_sm")) ctx->blocksPerSm = value;
     else if (!strcmp(key, "refill")) ctx->refill = value;
     else if (!strcmp(key, "simple_cfg")) ctx->simpleCfg = value;
-    else if (!strcmp(key, "bin_rays")) ctx->binRays = value;
-    else if (!strcmp(key, "bin_y") && value >= 1 && value <= 64) ctx->binY = value;
-    else if (!strcmp(key, "bin_t") && value >= 1 && value <= 1024) ctx->binT = value;
-    else if (!strcmp(key, "bin_p") && value >= 1 && value <= 1024) ctx->binP = value;
+    else if (!strncmp(key, "bin_", 4)) {
+        if (!strcmp(key, "bin_rays")) ctx->binRays = value;
+        else if (!strcmp(key, "bin_y") && value >= 1 && value <= 64) ctx->binY = value;
+        else if (!strcmp(key, "bin_t") && value >= 1 && value <= 1024) ctx->binT = value;
+        else if (!strcmp(key, "bin_p") && value >= 1 && value <= 1024) ctx->binP = value;
+        else return fail(ctx, UVRT_ERR_INVALID, "unknown option '%s' (or value %d out of range)", key, value);
+        if (ctx->countedRays >= 0 && ctx->dBinCount) {
+            // bin slots taken by the last generate belong to the old geometry: drop them
+            Bind b(ctx);
+            CK(cudaMemsetAsync(ctx->dBinCount, 0, (size_t)ctx->binCap * 4, ctx->stream));
+            ctx->countedRays = -1;
+        }
+    }
     else return fail(ctx, UVRT_ERR_INVALID, "unknown option '%s' (or value %d out of range)", key, value);
     return UVRT_OK;
 }

@@ -37,6 +37,23 @@ __device__ __forceinline__ F8 ldg256(const float4* p)
         : "l"(p));
     return r;
 }
+// The same 32 bytes as four 64-bit words: register pairs ready for the packed fp32x2 pipe.
+typedef unsigned long long u64;
+struct W4 { u64 w0, w1, w2, w3; };
+__device__ __forceinline__ W4 ldg256w(const float4* p)
+{
+    W4 r;
+    asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w0), "=l"(r.w1), "=l"(r.w2), "=l"(r.w3) : "l"(p));
+    return r;
+}
+// Packed binary32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): each half is an ordinary IEEE round-to-nearest
+// operation, so results are bit-identical to the scalar forms at half the issue slots.
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 // plain (coherent) 32-byte load for data written by an earlier kernel of the same stream
 __device__ __forceinline__ F8 ld256(const float4* p)
 {
@@ -106,8 +123,105 @@ __device__ __forceinline__ uint32_t generate_ray(int gid, float lx, float ly, fl
     return seed;
 }
 
+// ---- ray binning (queue re-ordering between generate and extend) --------------------------------
+// Rays of one launch leave the lamp in random directions; a warp of 32 consecutive rays walks 32
+// unrelated paths through the tree.  Before extend, rays are therefore ordered by a coarse key --
+// (dir.y cell, origin slice along the lamp, azimuth cell), azimuth varying fastest; the cells are
+// equal-probability for the lamp's uniform emission -- with a counting sort:
+//   count   one atomicAdd per ray on a 2^16-entry table (almost never contended) hands the ray its
+//           rank inside its bin; fused into generate while the ray is still in registers
+//   scan    64 blocks scan 1,024 counters each (and clear them for the next launch)
+//   scatter adds the prefix over the 64 block totals and writes the permutation
+// Extend then visits rays through the permutation and writes results back to the ray's own slot,
+// so the ray buffer keeps the reference's order and every per-ray result is unchanged.
+struct BinDims { int nY, nT, nP; float y0, invLen; };
+constexpr int kBinsPerScanBlock = 1024;
+
+__device__ __forceinline__ uint32_t bin_key(const BinDims& d, float dx, float dy, float dz, float oy)
+{
+    int t = min(d.nT - 1, max(0, (int)((dy + 1.0f) * 0.5f * (float)d.nT)));
+    int ph = min(d.nP - 1, max(0, (int)((atan2f(dz, dx) + 3.14159265f) * 0.159154943f * (float)d.nP)));
+    int y = min(d.nY - 1, max(0, (int)((oy - d.y0) * d.invLen * (float)d.nY)));
+    return (uint32_t)((t * d.nY + y) * d.nP + ph);
+}
+
+// for rays that were not produced by k_generate (uvrt_write)
+__global__ void __launch_bounds__(256) k_bin_count(const float4* __restrict__ rays, uint32_t nRays, BinDims d,
+                                                   unsigned int* __restrict__ binCount, uint2* __restrict__ keyRank)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nRays) return;
+    F8 r = ld256(rays + 2ull * i);
+    uint32_t key = bin_key(d, r.lo.x, r.lo.y, r.lo.z, r.hi.x);
+    uint32_t rank = atomicAdd(&binCount[key], 1u);
+    keyRank[i] = make_uint2(key, rank);
+}
+
+// One block scans kBinsPerScanBlock counters: binStart = exclusive scan inside the block's range,
+// blockTotal[blockIdx] = the range's sum; counters are cleared for the next launch.
+__global__ void __launch_bounds__(256) k_bin_scan(uint4* __restrict__ binCount, uint4* __restrict__ binStart,
+                                                  unsigned int* __restrict__ blockTotal)
+{
+    __shared__ unsigned int warpSums[8];
+    const int v4 = blockIdx.x * (kBinsPerScanBlock / 4) + threadIdx.x;   // one uint4 per thread
+    uint4 c = binCount[v4];
+    unsigned int local = c.x + c.y + c.z + c.w;
+    unsigned int v = local;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (unsigned)o) v += n;
+    }
+    if (lane == 31) warpSums[w] = v;
+    __syncthreads();
+    unsigned int before = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) before += (k < (int)w) ? warpSums[k] : 0u;
+    unsigned int run = before + v - local;
+    uint4 o;
+    o.x = run; run += c.x;
+    o.y = run; run += c.y;
+    o.z = run; run += c.z;
+    o.w = run; run += c.w;
+    binStart[v4] = o;
+    binCount[v4] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 255) blockTotal[blockIdx.x] = run;
+}
+
+__global__ void __launch_bounds__(256) k_bin_scatter(const uint2* __restrict__ keyRank, const unsigned int* __restrict__ binStart,
+                                                     const unsigned int* __restrict__ blockTotal, int nScanBlocks,
+                                                     uint32_t nRays, uint32_t* __restrict__ perm)
+{
+    __shared__ unsigned int blockBase[64];
+    __shared__ unsigned int first32Total;
+    if (threadIdx.x < 64) {
+        // exclusive prefix over the (at most 64) block totals, by two warps
+        unsigned int t = (int)threadIdx.x < nScanBlocks ? blockTotal[threadIdx.x] : 0u;
+        unsigned int v = t;
+        const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int n = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= (unsigned)o) v += n;
+        }
+        blockBase[threadIdx.x] = v - t;
+        if (threadIdx.x == 31) first32Total = v;
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32 && threadIdx.x < 64) blockBase[threadIdx.x] += first32Total;
+    __syncthreads();
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nRays) return;
+    uint2 kr = keyRank[i];
+    perm[binStart[kr.x] + blockBase[kr.x / kBinsPerScanBlock] + kr.y] = i;
+}
+
+// BIN = 1 also takes the ray's slot in its bin (the count step of the counting sort)
+template <int BIN>
 __global__ void __launch_bounds__(256) k_generate(float4* __restrict__ rays, long long firstRay, long long nRays,
-                                                  float lx, float ly, float lz, float lightLength, uint32_t seedIn)
+                                                  float lx, float ly, float lz, float lightLength, uint32_t seedIn,
+                                                  BinDims d, unsigned int* __restrict__ binCount, uint2* __restrict__ keyRank)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nRays) return;
@@ -115,6 +229,11 @@ __global__ void __launch_bounds__(256) k_generate(float4* __restrict__ rays, lon
     generate_ray((int)(firstRay + i), lx, ly, lz, lightLength, seedIn, r);
     rays[2 * i] = r.a;
     rays[2 * i + 1] = r.b;
+    if (BIN) {
+        uint32_t key = bin_key(d, r.a.x, r.a.y, r.a.z, r.b.x);
+        uint32_t rank = atomicAdd(&binCount[key], 1u);
+        keyRank[i] = make_uint2(key, rank);
+    }
 }
 
 // SEED chain (generate.cl:39): one thread replays work-item 0 of consecutive launches
@@ -148,7 +267,8 @@ enum DivMode { DIV_IEEE = 0, DIV_MARKSTEIN2 = 2, DIV_MARKSTEIN1 = 1 };
 
 struct RayCtx {
     float ox, oy, oz, dx, dy, dz;
-    float rx, ry, rz;     // RN(1/d) (Markstein modes)
+    // shared-reciprocal modes: (-o.x,-o.y) (-o.z,-o.z), RN(1/d) as (x,y) (z,z), (-d.x,-d.y) (-d.z,-d.z)
+    u64 noXY, noZZ, rXY, rZZ, ndXY, ndZZ;
     float dist;
     uint32_t tri;
 };
@@ -170,27 +290,88 @@ __device__ __forceinline__ float slab_q(float n, float d, float r)
     }
 }
 
-// extend.cl:29-38.  bmin/bmax carry the box in .xyz
+// the same quotient for two lanes at once: q = (a - o) / d with no = -o, nd = -d, r = RN(1/d)
 template <int DIV>
-__device__ __forceinline__ float intersect_aabb(const RayCtx& ray, const float4& bmin, const float4& bmax)
+__device__ __forceinline__ u64 slab_q2(u64 a, u64 no, u64 nd, u64 r)
 {
-    float tx1 = slab_q<DIV>(fs(bmin.x, ray.ox), ray.dx, ray.rx), tx2 = slab_q<DIV>(fs(bmax.x, ray.ox), ray.dx, ray.rx);
-    float ty1 = slab_q<DIV>(fs(bmin.y, ray.oy), ray.dy, ray.ry), ty2 = slab_q<DIV>(fs(bmax.y, ray.oy), ray.dy, ray.ry);
-    float tz1 = slab_q<DIV>(fs(bmin.z, ray.oz), ray.dz, ray.rz), tz2 = slab_q<DIV>(fs(bmax.z, ray.oz), ray.dz, ray.rz);
-    float tmin, tmax;
+    u64 n = add2(a, no);              // a + (-o) == a - o
+    u64 q = mul2(n, r);
+    u64 rem = fma2(nd, q, n);
+    q = fma2(rem, r, q);
+    if (DIV == DIV_MARKSTEIN2) {
+        rem = fma2(nd, q, n);
+        q = fma2(rem, r, q);
+    }
+    return q;
+}
+
+// extend.cl:29-38.  A child record is four 64-bit words:
+//   w0 = (min.x, min.y)   w1 = (max.x, max.y)   w2 = (min.z, max.z)   w3 = (reference, 0)
+// OCT >= 0 (shared-reciprocal modes only): the ray's direction signs are known at compile time
+// (bit 0/1/2 set = dir.x/y/z negative).  Division by a positive d is monotone, so with
+// box.min <= box.max (checked at upload) min(t1, t2) is t1 for d > 0 and t2 for d < 0: the six
+// per-axis min/max of extend.cl:32-36 disappear and tmin/tmax are one three-input max/min each.
+template <int DIV, int OCT>
+__device__ __forceinline__ bool intersect_aabb(const RayCtx& ray, const W4& c, float& tminOut)
+{
+    float tx1, ty1, tx2, ty2, tz1, tz2;
     if (DIV == DIV_IEEE) {
+        float mnx, mny, mxx, mxy, mnz, mxz;
+        upk2(c.w0, mnx, mny); upk2(c.w1, mxx, mxy); upk2(c.w2, mnz, mxz);
+        tx1 = __fdiv_rn(fs(mnx, ray.ox), ray.dx); tx2 = __fdiv_rn(fs(mxx, ray.ox), ray.dx);
+        ty1 = __fdiv_rn(fs(mny, ray.oy), ray.dy); ty2 = __fdiv_rn(fs(mxy, ray.oy), ray.dy);
+        tz1 = __fdiv_rn(fs(mnz, ray.oz), ray.dz); tz2 = __fdiv_rn(fs(mxz, ray.oz), ray.dz);
         // NaNs are possible here (0/0): keep OpenCL's select forms exactly
-        tmin = clmin(tx1, tx2); tmax = clmax(tx1, tx2);
+        float tmin = clmin(tx1, tx2), tmax = clmax(tx1, tx2);
         tmin = clmax(tmin, clmin(ty1, ty2)); tmax = clmin(tmax, clmax(ty1, ty2));
         tmin = clmax(tmin, clmin(tz1, tz2)); tmax = clmin(tmax, clmax(tz1, tz2));
+        tminOut = tmin;
+        return tmax >= tmin && tmin < ray.dist && tmax > 0.0f;
     } else {
+        upk2(slab_q2<DIV>(c.w0, ray.noXY, ray.ndXY, ray.rXY), tx1, ty1);
+        upk2(slab_q2<DIV>(c.w1, ray.noXY, ray.ndXY, ray.rXY), tx2, ty2);
+        upk2(slab_q2<DIV>(c.w2, ray.noZZ, ray.ndZZ, ray.rZZ), tz1, tz2);
         // tame rays produce no NaN; fminf/fmaxf then agree with the select forms up to the
         // sign of a zero, which no comparison below can observe
-        tmin = fminf(tx1, tx2); tmax = fmaxf(tx1, tx2);
-        tmin = fmaxf(tmin, fminf(ty1, ty2)); tmax = fminf(tmax, fmaxf(ty1, ty2));
-        tmin = fmaxf(tmin, fminf(tz1, tz2)); tmax = fminf(tmax, fmaxf(tz1, tz2));
+        float tmin, tmax;
+        if (OCT >= 0) {
+            const float nx = (OCT & 1) ? tx2 : tx1, fx = (OCT & 1) ? tx1 : tx2;
+            const float ny = (OCT & 2) ? ty2 : ty1, fy = (OCT & 2) ? ty1 : ty2;
+            const float nz = (OCT & 4) ? tz2 : tz1, fz = (OCT & 4) ? tz1 : tz2;
+            tmin = fmaxf(fmaxf(nx, ny), nz);
+            tmax = fminf(fminf(fx, fy), fz);
+        } else {
+            tmin = fminf(tx1, tx2); tmax = fmaxf(tx1, tx2);
+            tmin = fmaxf(tmin, fminf(ty1, ty2)); tmax = fminf(tmax, fmaxf(ty1, ty2));
+            tmin = fmaxf(tmin, fminf(tz1, tz2)); tmax = fminf(tmax, fmaxf(tz1, tz2));
+        }
+        tminOut = tmin;
+        return tmax >= tmin && tmin < ray.dist && tmax > 0.0f;
     }
-    return (tmax >= tmin && tmin < ray.dist && tmax > 0.0f) ? tmin : kNoHit;
+}
+
+// extend.cl:60-78 without materialising the 1e30f "miss" distances: with d = hit ? tmin : 1e30f
+// (tmin < dist <= 1e30f whenever hit), "d1 > d2" is h2 && (!h1 || tmin1 > tmin2).
+// Returns false when both children are missed; otherwise `first` is the child to enter and
+// `second` the one to push when pushSecond.
+__device__ __forceinline__ bool order_children(bool h1, bool h2, float t1, float t2, uint32_t c1, uint32_t c2,
+                                               uint32_t& first, uint32_t& second, bool& pushSecond)
+{
+    const bool swap = h2 && (!h1 || t1 > t2);
+    first = swap ? c2 : c1;
+    second = swap ? c1 : c2;
+    pushSecond = h1 && h2;
+    return h1 || h2;
+}
+
+__device__ __forceinline__ uint32_t child_ref(const W4& c) { return (uint32_t)c.w3; }
+
+__device__ __forceinline__ void make_tame(RayCtx& ray)
+{
+    float rx = __frcp_rn(ray.dx), ry = __frcp_rn(ray.dy), rz = __frcp_rn(ray.dz);
+    ray.noXY = pk2(-ray.ox, -ray.oy); ray.noZZ = pk2(-ray.oz, -ray.oz);
+    ray.rXY = pk2(rx, ry);            ray.rZZ = pk2(rz, rz);
+    ray.ndXY = pk2(-ray.dx, -ray.dy); ray.ndZZ = pk2(-ray.dz, -ray.dz);
 }
 
 // extend.cl:6-27 with edge1 = v1-v0 and edge2 = v2-v0 formed at upload time (the same IEEE
@@ -237,9 +418,9 @@ __device__ __forceinline__ bool ray_is_tame(const RayCtx& r)
 // extend.cl:40-81.  The traversal order, the tie rules (dist1 > dist2 swaps, so ties keep child
 // 1 first; strict t < dist keeps the first-found triangle) and the distance culling are the
 // reference's.  `pairs` holds, per inner node, its two children's boxes and references
-// (4 x float4); `wtris` holds leaf triangles in leaf order (4 x float4:
+// (2 x 32 bytes, see intersect_aabb); `wtris` holds leaf triangles in leaf order (4 x float4:
 // v0+tag, edge1, edge2, pad -- two 32-byte sectors).
-template <int DIV, int STACK>
+template <int DIV, int STACK, int OCT>
 __device__ __forceinline__ void bvh_intersect(RayCtx& ray, const float4* __restrict__ pairs,
                                               const float4* __restrict__ wtris, uint32_t rootRef)
 {
@@ -265,20 +446,18 @@ __device__ __forceinline__ void bvh_intersect(RayCtx& ray, const float4* __restr
             continue;
         }
         const float4* p = pairs + 4ull * cur;
-        F8 ca = ldg256(p), cb = ldg256(p + 2);
-        float d1 = intersect_aabb<DIV>(ray, ca.lo, ca.hi);
-        float d2 = intersect_aabb<DIV>(ray, cb.lo, cb.hi);
-        uint32_t c1 = __float_as_uint(ca.lo.w), c2 = __float_as_uint(cb.lo.w);
-        if (d1 > d2) {
-            float d = d1; d1 = d2; d2 = d;
-            uint32_t c = c1; c1 = c2; c2 = c;
-        }
-        if (d1 == kNoHit) {
+        W4 ca = ldg256w(p), cb = ldg256w(p + 2);
+        float t1, t2;
+        const bool h1 = intersect_aabb<DIV, OCT>(ray, ca, t1);
+        const bool h2 = intersect_aabb<DIV, OCT>(ray, cb, t2);
+        uint32_t first, second;
+        bool pushSecond;
+        if (order_children(h1, h2, t1, t2, child_ref(ca), child_ref(cb), first, second, pushSecond)) {
+            cur = first;
+            if (pushSecond) stack[sp++] = second;
+        } else {
             if (sp == 0) break;
             cur = stack[--sp];
-        } else {
-            cur = c1;
-            if (d2 != kNoHit) stack[sp++] = c2;
         }
     }
 }
@@ -288,15 +467,25 @@ __device__ __forceinline__ void trace_one(RayCtx& ray, const float4* __restrict_
                                           const float4* __restrict__ wtris, uint32_t rootRef, bool sceneTame)
 {
     if (DIV == DIV_IEEE) {
-        bvh_intersect<DIV_IEEE, STACK>(ray, pairs, wtris, rootRef);
+        bvh_intersect<DIV_IEEE, STACK, -1>(ray, pairs, wtris, rootRef);
     } else {
         if (sceneTame && ray_is_tame(ray)) {
-            ray.rx = __frcp_rn(ray.dx);
-            ray.ry = __frcp_rn(ray.dy);
-            ray.rz = __frcp_rn(ray.dz);
-            bvh_intersect<DIV, STACK>(ray, pairs, wtris, rootRef);
+            make_tame(ray);
+            // one specialised traversal loop per direction octant; binned rays make almost every
+            // warp octant-pure, so the switch rarely diverges
+            const int oct = (ray.dx < 0.0f ? 1 : 0) | (ray.dy < 0.0f ? 2 : 0) | (ray.dz < 0.0f ? 4 : 0);
+            switch (oct) {
+            case 0: bvh_intersect<DIV, STACK, 0>(ray, pairs, wtris, rootRef); break;
+            case 1: bvh_intersect<DIV, STACK, 1>(ray, pairs, wtris, rootRef); break;
+            case 2: bvh_intersect<DIV, STACK, 2>(ray, pairs, wtris, rootRef); break;
+            case 3: bvh_intersect<DIV, STACK, 3>(ray, pairs, wtris, rootRef); break;
+            case 4: bvh_intersect<DIV, STACK, 4>(ray, pairs, wtris, rootRef); break;
+            case 5: bvh_intersect<DIV, STACK, 5>(ray, pairs, wtris, rootRef); break;
+            case 6: bvh_intersect<DIV, STACK, 6>(ray, pairs, wtris, rootRef); break;
+            default: bvh_intersect<DIV, STACK, 7>(ray, pairs, wtris, rootRef); break;
+            }
         } else {
-            bvh_intersect<DIV_IEEE, STACK>(ray, pairs, wtris, rootRef);
+            bvh_intersect<DIV_IEEE, STACK, -1>(ray, pairs, wtris, rootRef);
         }
     }
 }
@@ -309,7 +498,7 @@ __device__ __forceinline__ void load_ray(const float4* __restrict__ rays, long l
     ray.ox = a.w; ray.oy = b.x; ray.oz = b.y;
     ray.dist = b.z;
     ray.tri = __float_as_uint(b.w);
-    ray.rx = ray.ry = ray.rz = 0.0f;
+    ray.noXY = ray.noZZ = ray.rXY = ray.rZZ = ray.ndXY = ray.ndZZ = 0ull;
 }
 
 __device__ __forceinline__ void store_hit(float4* __restrict__ rays, long long i, const RayCtx& ray)
@@ -317,93 +506,6 @@ __device__ __forceinline__ void store_hit(float4* __restrict__ rays, long long i
     // dist, triID occupy bytes 24..31 of the 32-byte ray record
     float2* p = reinterpret_cast<float2*>(rays + 2 * i + 1) + 1;
     *p = make_float2(ray.dist, __uint_as_float(ray.tri));
-}
-
-// ---- ray binning (queue re-ordering between generate and extend) --------------------------------
-// Rays of one launch leave the lamp in random directions; a warp of 32 consecutive rays walks 32
-// unrelated paths through the tree.  Before extend, rays are therefore ordered by a coarse key --
-// (origin slice along the lamp, dir.y cell, azimuth cell); the cells are equal-probability for the
-// lamp's uniform emission -- with a counting sort: k_bin_count takes a slot in the ray's bin
-// (one atomic per ray on a 2^16-entry table, so almost never contended), k_bin_scan turns counts
-// into offsets, k_bin_scatter writes the permutation.  Extend then visits rays through the
-// permutation and writes results back to the ray's own slot, so the ray buffer keeps the
-// reference's order and every per-ray result is unchanged.
-struct BinDims { int nY, nT, nP; float y0, invLen; };
-
-__device__ __forceinline__ uint32_t bin_key(const BinDims& d, float dx, float dy, float dz, float oy)
-{
-    int t = min(d.nT - 1, max(0, (int)((dy + 1.0f) * 0.5f * (float)d.nT)));
-    int ph = min(d.nP - 1, max(0, (int)((atan2f(dz, dx) + 3.14159265f) * 0.159154943f * (float)d.nP)));
-    int y = min(d.nY - 1, max(0, (int)((oy - d.y0) * d.invLen * (float)d.nY)));
-    return (uint32_t)((y * d.nT + t) * d.nP + ph);
-}
-
-__global__ void __launch_bounds__(256) k_bin_count(const float4* __restrict__ rays, uint32_t nRays, BinDims d,
-                                                   unsigned int* __restrict__ binCount, uint2* __restrict__ keyRank)
-{
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nRays) return;
-    F8 r = ld256(rays + 2ull * i);
-    uint32_t key = bin_key(d, r.lo.x, r.lo.y, r.lo.z, r.hi.x);
-    uint32_t rank = atomicAdd(&binCount[key], 1u);
-    keyRank[i] = make_uint2(key, rank);
-}
-
-// exclusive scan of nBins counters (nBins a multiple of 4096) by one block; also clears the
-// counters for the next launch.  Each thread owns nBins/1024 consecutive counters and moves them
-// as 16-byte vectors with all loads issued before the first use, so the whole scan costs a couple
-// of memory round trips instead of one per counter.
-template <int VEC>   // uint4 vectors per thread
-__global__ void __launch_bounds__(1024) k_bin_scan(uint4* __restrict__ binCount, uint4* __restrict__ binStart)
-{
-    __shared__ unsigned int warpSums[32];
-    uint4 c[VEC];
-    const int base4 = threadIdx.x * VEC;
-#pragma unroll
-    for (int k = 0; k < VEC; k++) c[k] = binCount[base4 + k];
-    unsigned int local = 0;
-#pragma unroll
-    for (int k = 0; k < VEC; k++) local += c[k].x + c[k].y + c[k].z + c[k].w;
-    unsigned int v = local;
-    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned int n = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= (unsigned)o) v += n;
-    }
-    if (lane == 31) warpSums[w] = v;
-    __syncthreads();
-    if (w == 0) {
-        unsigned int s = warpSums[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned int n = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= (unsigned)o) s += n;
-        }
-        warpSums[lane] = s;
-    }
-    __syncthreads();
-    unsigned int run = (v - local) + (w ? warpSums[w - 1] : 0u);
-    const uint4 zero = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int k = 0; k < VEC; k++) {
-        uint4 o;
-        o.x = run; run += c[k].x;
-        o.y = run; run += c[k].y;
-        o.z = run; run += c[k].z;
-        o.w = run; run += c[k].w;
-        binStart[base4 + k] = o;
-        binCount[base4 + k] = zero;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_bin_scatter(const uint2* __restrict__ keyRank, const unsigned int* __restrict__ binStart,
-                                                     uint32_t nRays, uint32_t* __restrict__ perm)
-{
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nRays) return;
-    uint2 kr = keyRank[i];
-    perm[binStart[kr.x] + kr.y] = i;
 }
 
 // Variant A: one thread per ray, the literal control flow of extend.cl:85-99.
@@ -460,7 +562,8 @@ k_extend_persist(int* __restrict__ counts, const float4* __restrict__ wtris, flo
     uint32_t stack[STACK];
     const unsigned lane = threadIdx.x & 31u;
     RayCtx ray;
-    ray.ox = ray.oy = ray.oz = ray.dx = ray.dy = ray.dz = ray.rx = ray.ry = ray.rz = 0.0f;
+    ray.ox = ray.oy = ray.oz = ray.dx = ray.dy = ray.dz = 0.0f;
+    ray.noXY = ray.noZZ = ray.rXY = ray.rZZ = ray.ndXY = ray.ndZZ = 0ull;
     ray.dist = kNoHit; ray.tri = 0;
     uint32_t cur = 0, rayIdx = 0xffffffffu;
     int sp = 0;
@@ -483,7 +586,7 @@ k_extend_persist(int* __restrict__ counts, const float4* __restrict__ wtris, flo
                     tame = false;
                     if (DIV != DIV_IEEE && sceneTame && ray_is_tame(ray)) {
                         tame = true;
-                        ray.rx = __frcp_rn(ray.dx); ray.ry = __frcp_rn(ray.dy); ray.rz = __frcp_rn(ray.dz);
+                        make_tame(ray);
                     }
                     cur = rootRef; sp = 0; busy = true;
                 }
@@ -499,25 +602,23 @@ k_extend_persist(int* __restrict__ counts, const float4* __restrict__ wtris, flo
 #pragma unroll 1
             for (int k = 0; k < K && busy && !(cur & kLeafFlag); k++) {
                 const float4* p = pairs + 4ull * cur;
-                F8 ca = ldg256(p), cb = ldg256(p + 2);
-                float d1, d2;
+                W4 ca = ldg256w(p), cb = ldg256w(p + 2);
+                float t1, t2;
+                bool h1, h2;
                 if (DIV == DIV_IEEE || !tame) {
-                    d1 = intersect_aabb<DIV_IEEE>(ray, ca.lo, ca.hi);
-                    d2 = intersect_aabb<DIV_IEEE>(ray, cb.lo, cb.hi);
+                    h1 = intersect_aabb<DIV_IEEE, -1>(ray, ca, t1);
+                    h2 = intersect_aabb<DIV_IEEE, -1>(ray, cb, t2);
                 } else {
-                    d1 = intersect_aabb<DIV>(ray, ca.lo, ca.hi);
-                    d2 = intersect_aabb<DIV>(ray, cb.lo, cb.hi);
+                    h1 = intersect_aabb<DIV, -1>(ray, ca, t1);
+                    h2 = intersect_aabb<DIV, -1>(ray, cb, t2);
                 }
-                uint32_t c1 = __float_as_uint(ca.lo.w), c2 = __float_as_uint(cb.lo.w);
-                if (d1 > d2) {
-                    float d = d1; d1 = d2; d2 = d;
-                    uint32_t c = c1; c1 = c2; c2 = c;
-                }
-                if (d1 == kNoHit) {
+                uint32_t first, second;
+                bool pushSecond;
+                if (order_children(h1, h2, t1, t2, child_ref(ca), child_ref(cb), first, second, pushSecond)) {
+                    cur = first;
+                    if (pushSecond) stack[sp++] = second;
+                } else {
                     if (sp == 0) busy = false; else cur = stack[--sp];
-                } else {
-                    cur = c1;
-                    if (d2 != kNoHit) stack[sp++] = c2;
                 }
             }
             if (busy && (cur & kLeafFlag)) {

@@ -41,6 +41,20 @@ def sorted_rays(gen, spec, lp, length):
         key = cell * nY + y
     elif mode == "ytp":
         key = (y * nT + t) * nP + ph
+    elif mode == "ytps":      # serpentine azimuth: neighbouring bins stay neighbours across rows
+        phs = np.where(t % 2 == 0, ph, nP - 1 - ph)
+        key = (y * nT + t) * nP + phs
+    elif mode == "morton3":   # interleave y, t, ph (equal bit counts expected)
+        def p3(x):
+            x = x.astype(np.uint64) & 0x3ff
+            x = (x | (x << 16)) & 0x30000ff
+            x = (x | (x << 8)) & 0x300f00f
+            x = (x | (x << 4)) & 0x30c30c3
+            x = (x | (x << 2)) & 0x9249249
+            return x
+        key = (p3(t) | (p3(ph) << 1) | (p3(y) << 2)).astype(np.int64)
+    elif mode == "tyq":       # direction cell major, then origin slice (fine), then azimuth
+        key = (t * nY + y) * nP + ph
     else:
         key = (t * nP + ph) * nY + y
     return gen[np.argsort(key, kind="stable")]
