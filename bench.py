@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--opt", action="append", default=[], help="backend option key=value (uvrt_set_option), repeatable")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -237,6 +238,9 @@ def main():
     ctx = sim.ctx
     if args.variant >= 0:
         ctx.set_option("extend_variant", args.variant)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     pos, p = sim.positions, sim.params
     L, P, n_tris = len(pos), int(p.photonsPerLight), room[0].shape[0]
     rays_per_pass = L * P
@@ -369,6 +373,7 @@ def main():
                    "timed": "generate+bin+extend+accumulate per position, computeDosage+dosageToColor (and the all-reduce) at the end of the run",
                    "l2": "flushed before every step (256 MiB memset on the same stream)",
                    "extend_variant": ctx.get_option("extend_variant"), "bin_rays": ctx.get_option("bin_rays"),
+                   "pipeline": ctx.get_option("pipeline"),
                    "parallelism": f"launches dealt round-robin to {n_gpus} GPU(s), one NCCL all-reduce per run"},
         "clocks": clk,
         "e2e": {"value": round(e2e_value, 1), "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -77,6 +77,24 @@ struct TimedLaunch {
     int stage;
 };
 
+// Everything that belongs to one launch's ray queue.
+struct RaySlot {
+    float4* dRays = nullptr;
+    long long rayCap = 0;
+    unsigned int* dBinCount = nullptr;
+    unsigned int* dBinStart = nullptr;
+    unsigned int* dBinBlock = nullptr;   // totals of the scan blocks
+    int binCap = 0, binUsed = 0;
+    long long countedRays = -1;          // rays whose bin slots k_generate already took (-1: none)
+    uint2* dKeyRank = nullptr;
+    uint32_t* dPerm = nullptr;
+    long long permCap = 0;
+    float binY0 = 0.0f, binLen = 1.0f;   // lamp extent of the rays in the buffer
+    bool binExtentKnown = false;
+    cudaEvent_t genDone = nullptr, freeEv = nullptr;
+    bool inFlight = false;               // freeEv has been recorded at least once
+};
+
 struct uvrt_ctx {
     int device = -1;
     cudaStream_t stream = nullptr;
@@ -97,27 +115,20 @@ struct uvrt_ctx {
     double* dMax = nullptr;
     float* dDose = nullptr;
     float* dColor = nullptr;
-    // rays
-    float4* dRays = nullptr;
-    long long rayCap = 0;
+    // rays: two slots, so that generate of the next launch can overlap extend of the current one
+    RaySlot slots[2];
+    int slot = 0;
+    RaySlot& rs() { return slots[slot]; }
+    cudaStream_t genStream = nullptr;    // generate (+ bin count) of pipelined uvrt_trace calls
+    int pipeline = 1;
     long long lastRays = 0;
     unsigned int* dQueue = nullptr;      // persistent-kernel work counter
     uint32_t* dSeeds = nullptr;
     float* dSeedPos = nullptr;
     int seedCap = 0;
     void* dFlush = nullptr;              // L2 flush scratch
-    // ray binning (counting sort by direction / origin cell)
-    unsigned int* dBinCount = nullptr;
-    unsigned int* dBinStart = nullptr;
-    unsigned int* dBinBlock = nullptr;   // totals of the scan blocks
-    int binCap = 0, binUsed = 0;
-    long long countedRays = -1;          // rays whose bin slots k_generate already took (-1: none)
-    uint2* dKeyRank = nullptr;
-    uint32_t* dPerm = nullptr;
-    long long permCap = 0;
+    // ray binning (counting sort by direction / origin cell); the tables live in the ray slots
     int binRays = 1, binY = 16, binT = 32, binP = 128;   // 65,536 bins: best of the sweeps
-    float binY0 = 0.0f, binLen = 1.0f;   // lamp extent of the rays in the buffer
-    bool binExtentKnown = false;
     int64_t uploadBytes = 0;
     // pinned staging for the scene upload, and scratch that survives between uploads
     void* hStage = nullptr;
@@ -188,18 +199,19 @@ struct StageTimer {
     uvrt_ctx* ctx;
     TimedLaunch t{};
     bool on;
-    StageTimer(uvrt_ctx* c, int stage) : ctx(c), on(c->stageTiming != 0)
+    cudaStream_t stream;
+    StageTimer(uvrt_ctx* c, int stage, cudaStream_t st = nullptr) : ctx(c), on(c->stageTiming != 0), stream(st ? st : c->stream)
     {
         if (!on) return;
         t.stage = stage;
         t.start = get_event(c);
         t.stop = get_event(c);
-        cudaEventRecord(t.start, c->stream);
+        cudaEventRecord(t.start, stream);
     }
     ~StageTimer()
     {
         if (!on) return;
-        cudaEventRecord(t.stop, ctx->stream);
+        cudaEventRecord(t.stop, stream);
         ctx->timed.push_back(t);
     }
 };
@@ -215,12 +227,12 @@ int dev_alloc(uvrt_ctx* ctx, T** p, size_t count)
 
 int ensure_rays(uvrt_ctx* ctx, long long nRays)
 {
-    if (nRays <= ctx->rayCap) return UVRT_OK;
+    if (nRays <= ctx->rs().rayCap) return UVRT_OK;
     // raytracer.cpp:137 sizes the ray buffer by photonCount; here it follows the largest launch
     long long cap = std::max<long long>(nRays, 1 << 16);
-    if (ctx->dRays) { cudaFree(ctx->dRays); ctx->dRays = nullptr; ctx->rayCap = 0; }
-    CK(cudaMalloc((void**)&ctx->dRays, (size_t)cap * 32));
-    ctx->rayCap = cap;
+    if (ctx->rs().dRays) { cudaFree(ctx->rs().dRays); ctx->rs().dRays = nullptr; ctx->rs().rayCap = 0; }
+    CK(cudaMalloc((void**)&ctx->rs().dRays, (size_t)cap * 32));
+    ctx->rs().rayCap = cap;
     return UVRT_OK;
 }
 
@@ -230,14 +242,14 @@ struct HostNode { float mn[3]; uint32_t leftFirst; float mx[3]; uint32_t triCoun
 bool coord_tame(float v)
 {
     float a = std::fabs(v);
-    return a == 0.0f || (a >= 9.5367431640625e-07f && a <= 1048576.0f);
+    return a == 0.0f || (a >= 6.6174449e-24f && a <= 1048576.0f);   // 0 or [2^-77, 2^20], see ray_is_tame()
 }
 
 int check_buffer(uvrt_ctx* ctx, uvrt_buffer what, void** ptr, size_t* bytes)
 {
     size_t n = (size_t)ctx->nTris;
     switch (what) {
-    case UVRT_BUF_RAYS: *ptr = ctx->dRays; *bytes = (size_t)ctx->rayCap * 32; return UVRT_OK;
+    case UVRT_BUF_RAYS: *ptr = ctx->rs().dRays; *bytes = (size_t)ctx->rs().rayCap * 32; return UVRT_OK;
     case UVRT_BUF_COUNTS: *ptr = ctx->dCounts; *bytes = n * 4; return UVRT_OK;
     case UVRT_BUF_SUM: *ptr = ctx->dSum; *bytes = n * 8; return UVRT_OK;
     case UVRT_BUF_MAX: *ptr = ctx->dMax; *bytes = n * 8; return UVRT_OK;
@@ -263,7 +275,7 @@ template <int DIV, int THREADS, int MINB>
 void launch_simple_cfg(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
     k_extend_simple<DIV, kStack, THREADS, MINB><<<grid_for(nRays, THREADS), THREADS, 0, ctx->stream>>>(
-        ctx->dCounts, ctx->dWtris, ctx->dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm);
+        ctx->dCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm);
 }
 
 template <int DIV>
@@ -291,7 +303,7 @@ void launch_persist_r(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     long long needed = (nRays + THREADS - 1) / THREADS;
     if (blocks > needed) blocks = needed;
     cudaMemsetAsync(ctx->dQueue, 0, sizeof(unsigned int), ctx->stream);
-    kern<<<(unsigned)blocks, THREADS, 0, ctx->stream>>>(ctx->dCounts, ctx->dWtris, ctx->dRays, ctx->dPairs,
+    kern<<<(unsigned)blocks, THREADS, 0, ctx->stream>>>(ctx->dCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs,
                                                         ctx->rootRef, (uint32_t)nRays, ctx->sceneTame, ctx->dQueue, perm);
 }
 
@@ -321,7 +333,7 @@ void launch_persist_d(uvrt_ctx* ctx, long long nRays, int d, const uint32_t* per
 
 // Counting sort of the ray queue (kernels: uvrt_kernels.cuh "ray binning").  bin_prepare sizes the
 // tables; the count step runs inside k_generate (countedRays) or as k_bin_count; bin_finish scans and
-// scatters, leaving the permutation in ctx->dPerm.
+// scatters, leaving the permutation in ctx->rs().dPerm.
 int bin_prepare(uvrt_ctx* ctx, long long nRays, BinDims* d)
 {
     const int wanted = ctx->binY * ctx->binT * ctx->binP;
@@ -329,53 +341,53 @@ int bin_prepare(uvrt_ctx* ctx, long long nRays, BinDims* d)
     while (nBins < wanted) nBins *= 2;
     if (nBins > 64 * kBinsPerScanBlock)
         return fail(ctx, UVRT_ERR_INVALID, "bin_y*bin_t*bin_p = %d exceeds the supported %d bins", wanted, 64 * kBinsPerScanBlock);
-    if (nBins > ctx->binCap) {
-        if (ctx->dBinCount) cudaFree(ctx->dBinCount);
-        if (ctx->dBinStart) cudaFree(ctx->dBinStart);
-        if (ctx->dBinBlock) cudaFree(ctx->dBinBlock);
-        ctx->dBinCount = ctx->dBinStart = ctx->dBinBlock = nullptr;
-        ctx->binCap = 0;
-        CK(cudaMalloc((void**)&ctx->dBinCount, (size_t)nBins * 4));
-        CK(cudaMalloc((void**)&ctx->dBinStart, (size_t)nBins * 4));
-        CK(cudaMalloc((void**)&ctx->dBinBlock, 64 * 4));
-        CK(cudaMemsetAsync(ctx->dBinCount, 0, (size_t)nBins * 4, ctx->stream));
-        ctx->binCap = nBins;
+    if (nBins > ctx->rs().binCap) {
+        if (ctx->rs().dBinCount) cudaFree(ctx->rs().dBinCount);
+        if (ctx->rs().dBinStart) cudaFree(ctx->rs().dBinStart);
+        if (ctx->rs().dBinBlock) cudaFree(ctx->rs().dBinBlock);
+        ctx->rs().dBinCount = ctx->rs().dBinStart = ctx->rs().dBinBlock = nullptr;
+        ctx->rs().binCap = 0;
+        CK(cudaMalloc((void**)&ctx->rs().dBinCount, (size_t)nBins * 4));
+        CK(cudaMalloc((void**)&ctx->rs().dBinStart, (size_t)nBins * 4));
+        CK(cudaMalloc((void**)&ctx->rs().dBinBlock, 64 * 4));
+        CK(cudaMemset(ctx->rs().dBinCount, 0, (size_t)nBins * 4));   // rare: synchronous on purpose
+        ctx->rs().binCap = nBins;
     }
-    ctx->binUsed = nBins;
-    if (nRays > ctx->permCap) {
-        if (ctx->dKeyRank) cudaFree(ctx->dKeyRank);
-        if (ctx->dPerm) cudaFree(ctx->dPerm);
-        ctx->dKeyRank = nullptr; ctx->dPerm = nullptr; ctx->permCap = 0;
-        CK(cudaMalloc((void**)&ctx->dKeyRank, (size_t)ctx->rayCap * 8));
-        CK(cudaMalloc((void**)&ctx->dPerm, (size_t)ctx->rayCap * 4));
-        ctx->permCap = ctx->rayCap;
+    ctx->rs().binUsed = nBins;
+    if (nRays > ctx->rs().permCap) {
+        if (ctx->rs().dKeyRank) cudaFree(ctx->rs().dKeyRank);
+        if (ctx->rs().dPerm) cudaFree(ctx->rs().dPerm);
+        ctx->rs().dKeyRank = nullptr; ctx->rs().dPerm = nullptr; ctx->rs().permCap = 0;
+        CK(cudaMalloc((void**)&ctx->rs().dKeyRank, (size_t)ctx->rs().rayCap * 8));
+        CK(cudaMalloc((void**)&ctx->rs().dPerm, (size_t)ctx->rs().rayCap * 4));
+        ctx->rs().permCap = ctx->rs().rayCap;
     }
-    d->nY = ctx->binExtentKnown ? ctx->binY : 1;
+    d->nY = ctx->rs().binExtentKnown ? ctx->binY : 1;
     d->nT = ctx->binT;
     d->nP = ctx->binP;
-    d->y0 = ctx->binY0;
-    d->invLen = ctx->binLen > 0.0f ? 1.0f / ctx->binLen : 0.0f;
+    d->y0 = ctx->rs().binY0;
+    d->invLen = ctx->rs().binLen > 0.0f ? 1.0f / ctx->rs().binLen : 0.0f;
     return UVRT_OK;
 }
 
 int bin_finish(uvrt_ctx* ctx, long long nRays)
 {
     StageTimer t(ctx, UVRT_STAGE_BIN);
-    if (ctx->countedRays != nRays) {
+    if (ctx->rs().countedRays != nRays) {
         // the rays in the buffer did not (all) come from k_generate<1>: count them now
         BinDims d;
         int rc = bin_prepare(ctx, nRays, &d);
         if (rc) return rc;
-        if (ctx->countedRays >= 0) CK(cudaMemsetAsync(ctx->dBinCount, 0, (size_t)ctx->binCap * 4, ctx->stream));
-        k_bin_count<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dRays, (uint32_t)nRays, d, ctx->dBinCount, ctx->dKeyRank);
+        if (ctx->rs().countedRays >= 0) CK(cudaMemsetAsync(ctx->rs().dBinCount, 0, (size_t)ctx->rs().binCap * 4, ctx->stream));
+        k_bin_count<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->rs().dRays, (uint32_t)nRays, d, ctx->rs().dBinCount, ctx->rs().dKeyRank);
         ctx->launches++;
     }
-    ctx->countedRays = -1;
-    const int nScanBlocks = ctx->binUsed / kBinsPerScanBlock;
-    k_bin_scan<<<nScanBlocks, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(ctx->dBinCount),
-                                                     reinterpret_cast<uint4*>(ctx->dBinStart), ctx->dBinBlock);
-    k_bin_scatter<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dKeyRank, ctx->dBinStart, ctx->dBinBlock, nScanBlocks,
-                                                                 (uint32_t)nRays, ctx->dPerm);
+    ctx->rs().countedRays = -1;
+    const int nScanBlocks = ctx->rs().binUsed / kBinsPerScanBlock;
+    k_bin_scan<<<nScanBlocks, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(ctx->rs().dBinCount),
+                                                     reinterpret_cast<uint4*>(ctx->rs().dBinStart), ctx->rs().dBinBlock);
+    k_bin_scatter<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->rs().dKeyRank, ctx->rs().dBinStart, ctx->rs().dBinBlock, nScanBlocks,
+                                                                 (uint32_t)nRays, ctx->rs().dPerm);
     ctx->launches += 2;
     return UVRT_OK;
 }
@@ -441,6 +453,17 @@ int uvrt_create(uvrt_ctx** out, int device)
     cudaGetDevice(&prev);
     cudaSetDevice(device);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        // higher priority: generate's blocks are placed as soon as extend's blocks retire, so the two
+        // really run side by side instead of generate waiting for extend's last wave
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&ctx->genStream, cudaStreamNonBlocking, hi);
+    }
+    for (RaySlot& r : ctx->slots) {
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.genDone, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.freeEv, cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->dQueue, 256);
     for (int i = 0; i < 16 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->marks[i]);
     if (prev >= 0 && prev != device) cudaSetDevice(prev);
@@ -457,12 +480,19 @@ void uvrt_destroy(uvrt_ctx* ctx)
 {
     if (!ctx) return;
     Bind b(ctx);
+    if (ctx->genStream) cudaStreamSynchronize(ctx->genStream);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     void* ptrs[] = {ctx->dPairs, ctx->dWtris, ctx->dVerts, ctx->dCounts, ctx->dSum, ctx->dMax, ctx->dDose,
-                    ctx->dColor, ctx->dRays, ctx->dQueue, ctx->dSeeds, ctx->dSeedPos, ctx->dFlush,
-                    ctx->dBinCount, ctx->dBinStart, ctx->dBinBlock, ctx->dKeyRank, ctx->dPerm};
+                    ctx->dColor, ctx->dQueue, ctx->dSeeds, ctx->dSeedPos, ctx->dFlush};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (RaySlot& r : ctx->slots) {
+        void* q[] = {r.dRays, r.dBinCount, r.dBinStart, r.dBinBlock, r.dKeyRank, r.dPerm};
+        for (void* p : q) if (p) cudaFree(p);
+        if (r.genDone) cudaEventDestroy(r.genDone);
+        if (r.freeEv) cudaEventDestroy(r.freeEv);
+    }
+    if (ctx->genStream) cudaStreamDestroy(ctx->genStream);
     if (ctx->hStage) cudaFreeHost(ctx->hStage);
     for (auto& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
     for (auto e : ctx->freeEvents) cudaEventDestroy(e);
@@ -548,12 +578,17 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
     float* hp = (float*)ctx->hStage;
     float* hw = (float*)((char*)ctx->hStage + pairBytes);
     float* hv = (float*)((char*)ctx->hStage + pairBytes + wtriBytes);
-    memset(hp, 0, pairBytes);
+    if (nPairs == 0) memset(hp, 0, pairBytes);
     bool tame = true;
     auto child_ref = [&](uint32_t n) -> uint32_t {
         return nodes[n].triCount > 0 ? (kLeafFlag | (uint32_t)id[n]) : (uint32_t)id[n];
     };
-    for (uint32_t n : order) {
+    // every reachable node fills its own record: independent, so spread over the host cores
+    int tameAll = 1;
+    const long long nOrder = (long long)order.size();
+#pragma omp parallel for schedule(static) reduction(&& : tameAll) if (nOrder > 4096)
+    for (long long oi = 0; oi < nOrder; oi++) {
+        const uint32_t n = order[oi];
         const HostNode& nd = nodes[n];
         if (nd.triCount > 0) {
             for (uint32_t k = 0; k < nd.triCount; k++) {
@@ -580,10 +615,12 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
                 memcpy(&q[6], &ref, 4);
                 q[7] = 0.0f;
                 // the fast box test needs normal-range coordinates and min <= max on every axis
-                for (int a = 0; a < 3; a++) tame = tame && coord_tame(ch.mn[a]) && coord_tame(ch.mx[a]) && ch.mn[a] <= ch.mx[a];
+                for (int a = 0; a < 3; a++)
+                    tameAll = tameAll && coord_tame(ch.mn[a]) && coord_tame(ch.mx[a]) && ch.mn[a] <= ch.mx[a];
             }
         }
     }
+    tame = tameAll != 0;
     memcpy(hv, tris, vertBytes);
 
     // ---- device buffers -------------------------------------------------------------------------
@@ -660,43 +697,55 @@ int uvrt_reset(uvrt_ctx* ctx, int resetColor)
     return UVRT_OK;
 }
 
-int uvrt_generate(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, int64_t firstRay, int64_t nRays,
-                  uint32_t seedIn)
+// generate (+ the count step of the binning) into the current ray slot, on `stream`
+static int generate_on(uvrt_ctx* ctx, cudaStream_t stream, float lx, float ly, float lz, float lightLength,
+                       int64_t firstRay, int64_t nRays, uint32_t seedIn)
 {
-    NEED_SCENE();
     if (nRays < 0 || firstRay < 0 || nRays > 0x7fffffffll)
         return fail(ctx, UVRT_ERR_INVALID, "generate: bad ray range first=%lld n=%lld", (long long)firstRay, (long long)nRays);
     int rc = ensure_rays(ctx, nRays);
     if (rc) return rc;
+    RaySlot& S = ctx->rs();
     ctx->lastRays = nRays;
-    ctx->binY0 = ly;
-    ctx->binLen = lightLength;
-    ctx->binExtentKnown = true;
-    ctx->countedRays = -1;
+    S.binY0 = ly;
+    S.binLen = lightLength;
+    S.binExtentKnown = true;
+    if (S.countedRays >= 0) {
+        // slots taken by a generate whose rays were never extended
+        CK(cudaMemsetAsync(S.dBinCount, 0, (size_t)S.binCap * 4, stream));
+        S.countedRays = -1;
+    }
     if (nRays == 0) return UVRT_OK;
     if (ctx->binRays && nRays >= kMinRaysForBinning) {
         BinDims d;
         rc = bin_prepare(ctx, nRays, &d);
         if (rc) return rc;
-        StageTimer t(ctx, UVRT_STAGE_GENERATE);
-        k_generate<1><<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dRays, firstRay, nRays, lx, ly, lz, lightLength, seedIn,
-                                                                      d, ctx->dBinCount, ctx->dKeyRank);
-        ctx->countedRays = nRays;
+        StageTimer t(ctx, UVRT_STAGE_GENERATE, stream);
+        k_generate<1><<<grid_for(nRays, 256), 256, 0, stream>>>(S.dRays, firstRay, nRays, lx, ly, lz, lightLength, seedIn,
+                                                                 d, S.dBinCount, S.dKeyRank);
+        S.countedRays = nRays;
     } else {
-        StageTimer t(ctx, UVRT_STAGE_GENERATE);
-        k_generate<0><<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->dRays, firstRay, nRays, lx, ly, lz, lightLength, seedIn,
-                                                                      BinDims{1, 1, 1, 0.0f, 0.0f}, nullptr, nullptr);
+        StageTimer t(ctx, UVRT_STAGE_GENERATE, stream);
+        k_generate<0><<<grid_for(nRays, 256), 256, 0, stream>>>(S.dRays, firstRay, nRays, lx, ly, lz, lightLength, seedIn,
+                                                                 BinDims{1, 1, 1, 0.0f, 0.0f}, nullptr, nullptr);
     }
     ctx->launches++;
     CK_LAUNCH("generate");
     return UVRT_OK;
 }
 
+int uvrt_generate(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, int64_t firstRay, int64_t nRays,
+                  uint32_t seedIn)
+{
+    NEED_SCENE();
+    return generate_on(ctx, ctx->stream, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
+}
+
 int uvrt_extend(uvrt_ctx* ctx, int64_t nRays)
 {
     NEED_SCENE();
-    if (nRays < 0 || nRays > ctx->rayCap)
-        return fail(ctx, UVRT_ERR_INVALID, "extend: nRays=%lld exceeds the ray buffer (%lld)", (long long)nRays, ctx->rayCap);
+    if (nRays < 0 || nRays > ctx->rs().rayCap)
+        return fail(ctx, UVRT_ERR_INVALID, "extend: nRays=%lld exceeds the ray buffer (%lld)", (long long)nRays, ctx->rs().rayCap);
     if (nRays == 0) return UVRT_OK;
     int rc;
     const uint32_t* perm = nullptr;
@@ -705,11 +754,11 @@ int uvrt_extend(uvrt_ctx* ctx, int64_t nRays)
         rc = bin_finish(ctx, nRays);
         if (rc) return rc;
         CK_LAUNCH("bin");
-        perm = ctx->dPerm;
-    } else if (ctx->countedRays >= 0) {
+        perm = ctx->rs().dPerm;
+    } else if (ctx->rs().countedRays >= 0) {
         // binning was switched off between generate and extend: drop the slots generate took
-        CK(cudaMemsetAsync(ctx->dBinCount, 0, (size_t)ctx->binCap * 4, ctx->stream));
-        ctx->countedRays = -1;
+        CK(cudaMemsetAsync(ctx->rs().dBinCount, 0, (size_t)ctx->rs().binCap * 4, ctx->stream));
+        ctx->rs().countedRays = -1;
     }
     {
         StageTimer t(ctx, UVRT_STAGE_EXTEND);
@@ -735,9 +784,27 @@ int uvrt_accumulate(uvrt_ctx* ctx, float duration)
 int uvrt_trace_counts(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, int64_t firstRay, int64_t nRays,
                       uint32_t seedIn)
 {
-    int rc = uvrt_generate(ctx, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
+    NEED_SCENE();
+    if (!ctx->pipeline) {
+        int rc = generate_on(ctx, ctx->stream, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
+        if (rc) return rc;
+        return uvrt_extend(ctx, nRays);
+    }
+    // Pipelined: this launch's rays go to the other slot and are generated on the second stream, so
+    // generate (HBM-bound) overlaps the extend of the previous launch (issue-bound) still running on
+    // the main stream.  Everything after generate stays on the main stream in the reference's order.
+    ctx->slot ^= 1;
+    RaySlot& S = ctx->rs();
+    if (S.inFlight) CK(cudaStreamWaitEvent(ctx->genStream, S.freeEv, 0));   // the extend that last read this slot
+    int rc = generate_on(ctx, ctx->genStream, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
     if (rc) return rc;
-    return uvrt_extend(ctx, nRays);
+    CK(cudaEventRecord(S.genDone, ctx->genStream));
+    CK(cudaStreamWaitEvent(ctx->stream, S.genDone, 0));
+    rc = uvrt_extend(ctx, nRays);
+    if (rc) return rc;
+    CK(cudaEventRecord(S.freeEv, ctx->stream));
+    S.inFlight = true;
+    return UVRT_OK;
 }
 
 int uvrt_trace(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, float duration, int64_t firstRay,
@@ -819,10 +886,10 @@ int uvrt_write(uvrt_ctx* ctx, uvrt_buffer what, const void* src, size_t bytes)
         int rc = ensure_rays(ctx, (long long)((bytes + 31) / 32));
         if (rc) return rc;
         ctx->lastRays = (long long)(bytes / 32);
-        ctx->binExtentKnown = false;   // foreign rays: no origin slicing
-        if (ctx->countedRays >= 0 && ctx->dBinCount) {
-            CK(cudaMemsetAsync(ctx->dBinCount, 0, (size_t)ctx->binCap * 4, ctx->stream));
-            ctx->countedRays = -1;
+        ctx->rs().binExtentKnown = false;   // foreign rays: no origin slicing
+        if (ctx->rs().countedRays >= 0 && ctx->rs().dBinCount) {
+            CK(cudaMemsetAsync(ctx->rs().dBinCount, 0, (size_t)ctx->rs().binCap * 4, ctx->stream));
+            ctx->rs().countedRays = -1;
         }
     }
     void* p = nullptr;
@@ -839,6 +906,7 @@ int uvrt_sync(uvrt_ctx* ctx)
 {
     if (!ctx) return UVRT_ERR_INVALID;
     Bind b(ctx);
+    CK(cudaStreamSynchronize(ctx->genStream));
     CK(cudaStreamSynchronize(ctx->stream));
     return UVRT_OK;
 }
@@ -904,17 +972,18 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
     else if (!strcmp(key, "blocks_per_sm")) ctx->blocksPerSm = value;
     else if (!strcmp(key, "refill")) ctx->refill = value;
     else if (!strcmp(key, "simple_cfg")) ctx->simpleCfg = value;
+    else if (!strcmp(key, "pipeline")) ctx->pipeline = value;
     else if (!strncmp(key, "bin_", 4)) {
         if (!strcmp(key, "bin_rays")) ctx->binRays = value;
         else if (!strcmp(key, "bin_y") && value >= 1 && value <= 64) ctx->binY = value;
         else if (!strcmp(key, "bin_t") && value >= 1 && value <= 1024) ctx->binT = value;
         else if (!strcmp(key, "bin_p") && value >= 1 && value <= 1024) ctx->binP = value;
         else return fail(ctx, UVRT_ERR_INVALID, "unknown option '%s' (or value %d out of range)", key, value);
-        if (ctx->countedRays >= 0 && ctx->dBinCount) {
+        if (ctx->rs().countedRays >= 0 && ctx->rs().dBinCount) {
             // bin slots taken by the last generate belong to the old geometry: drop them
             Bind b(ctx);
-            CK(cudaMemsetAsync(ctx->dBinCount, 0, (size_t)ctx->binCap * 4, ctx->stream));
-            ctx->countedRays = -1;
+            CK(cudaMemsetAsync(ctx->rs().dBinCount, 0, (size_t)ctx->rs().binCap * 4, ctx->stream));
+            ctx->rs().countedRays = -1;
         }
     }
     else return fail(ctx, UVRT_ERR_INVALID, "unknown option '%s' (or value %d out of range)", key, value);
@@ -931,6 +1000,7 @@ int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value)
     else if (!strcmp(key, "scene_tame")) *value = ctx->sceneTame;
     else if (!strcmp(key, "refill")) *value = ctx->refill;
     else if (!strcmp(key, "simple_cfg")) *value = ctx->simpleCfg;
+    else if (!strcmp(key, "pipeline")) *value = ctx->pipeline;
     else if (!strcmp(key, "bin_rays")) *value = ctx->binRays;
     else if (!strcmp(key, "bin_y")) *value = ctx->binY;
     else if (!strcmp(key, "bin_t")) *value = ctx->binT;
@@ -987,6 +1057,8 @@ int uvrt_mark(uvrt_ctx* ctx, int slot)
     if (!ctx || slot < 0 || slot >= 16) return UVRT_ERR_INVALID;
     Bind b(ctx);
     CK(cudaEventRecord(ctx->marks[slot], ctx->stream));
+    // work of later calls on the second stream must not start before the mark
+    CK(cudaStreamWaitEvent(ctx->genStream, ctx->marks[slot], 0));
     return UVRT_OK;
 }
 

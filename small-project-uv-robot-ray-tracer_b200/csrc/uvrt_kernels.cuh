@@ -383,7 +383,7 @@ __device__ __forceinline__ void intersect_tri(RayCtx& ray, const float4& t0, con
     float hz = fs(fm(ray.dx, e2.y), fm(ray.dy, e2.x));
     float a = fa(fa(fm(e1.x, hx), fm(e1.y, hy)), fm(e1.z, hz));
     if (fabsf(a) < 0.00001f) return;
-    float f = __fdiv_rn(1.0f, a);
+    float f = __frcp_rn(a);           // RN(1/a): the same value as the division 1 / a of extend.cl:17
     float sx = fs(ray.ox, t0.x), sy = fs(ray.oy, t0.y), sz = fs(ray.oz, t0.z);
     float u = fm(f, fa(fa(fm(sx, hx), fm(sy, hy)), fm(sz, hz)));
     if ((u < 0.0f) | (u > 1.0f)) return;
@@ -399,14 +399,16 @@ __device__ __forceinline__ void intersect_tri(RayCtx& ray, const float4& t0, con
     }
 }
 
-// A ray is "tame" when the Markstein quotient provably equals the IEEE one for every box of a
-// scene whose coordinates are 0 or >= 2^-20 in magnitude (checked at upload): direction
-// components in [2^-30, 2], origin components 0 or >= 2^-20.  Then n = a - o is 0 or >= 2^-43,
-// |q| <= 2^36, and the residual fma(-d, q, n) is exact and far from the denormal range.
+// A ray is "tame" when every intermediate of the shared-reciprocal quotient stays exactly
+// representable, for every box of a scene whose coordinates are 0 or in [2^-77, 2^20] in magnitude
+// (checked at upload): direction components in [2^-30, 2], origin components 0 or in [2^-77, 2^20].
+// Then n = a - o is 0 or >= 2^-100 (a difference of two floats is a multiple of the smaller ulp),
+// q0 = n*r >= 2^-101 is normal, the residual n - d*q0 is a multiple of 2^(e_n - 47) >= 2^-149 and so
+// exact even when denormal (no flush-to-zero in this build), and |q| <= 2^51.
 __device__ __forceinline__ bool ray_is_tame(const RayCtx& r)
 {
     const float dlo = 9.31322574615478515625e-10f;  // 2^-30
-    const float olo = 9.5367431640625e-07f;         // 2^-20
+    const float olo = 6.6174449e-24f;               // 2^-77
     float ax = fabsf(r.dx), ay = fabsf(r.dy), az = fabsf(r.dz);
     bool d_ok = ax >= dlo && ay >= dlo && az >= dlo && ax <= 2.0f && ay <= 2.0f && az <= 2.0f;
     float px = fabsf(r.ox), py = fabsf(r.oy), pz = fabsf(r.oz);
@@ -464,7 +466,7 @@ __device__ __forceinline__ void bvh_intersect(RayCtx& ray, const float4* __restr
 
 template <int DIV, int STACK>
 __device__ __forceinline__ void trace_one(RayCtx& ray, const float4* __restrict__ pairs,
-                                          const float4* __restrict__ wtris, uint32_t rootRef, bool sceneTame)
+                                          const float4* __restrict__ wtris, uint32_t rootRef, bool sceneTame, bool binned)
 {
     if (DIV == DIV_IEEE) {
         bvh_intersect<DIV_IEEE, STACK, -1>(ray, pairs, wtris, rootRef);
@@ -472,9 +474,11 @@ __device__ __forceinline__ void trace_one(RayCtx& ray, const float4* __restrict_
         if (sceneTame && ray_is_tame(ray)) {
             make_tame(ray);
             // one specialised traversal loop per direction octant; binned rays make almost every
-            // warp octant-pure, so the switch rarely diverges
-            const int oct = (ray.dx < 0.0f ? 1 : 0) | (ray.dy < 0.0f ? 2 : 0) | (ray.dz < 0.0f ? 4 : 0);
+            // warp octant-pure, so the switch rarely diverges.  Unsorted rays would serialise all
+            // eight loops in every warp: they take the generic loop (-1).
+            const int oct = !binned ? -1 : (ray.dx < 0.0f ? 1 : 0) | (ray.dy < 0.0f ? 2 : 0) | (ray.dz < 0.0f ? 4 : 0);
             switch (oct) {
+            case -1: bvh_intersect<DIV, STACK, -1>(ray, pairs, wtris, rootRef); break;
             case 0: bvh_intersect<DIV, STACK, 0>(ray, pairs, wtris, rootRef); break;
             case 1: bvh_intersect<DIV, STACK, 1>(ray, pairs, wtris, rootRef); break;
             case 2: bvh_intersect<DIV, STACK, 2>(ray, pairs, wtris, rootRef); break;
@@ -520,7 +524,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_extend_simple(int* __res
     if (perm) i = perm[i];
     RayCtx ray;
     load_ray(rays, i, ray);
-    trace_one<DIV, STACK>(ray, pairs, wtris, rootRef, sceneTame != 0);
+    trace_one<DIV, STACK>(ray, pairs, wtris, rootRef, sceneTame != 0, perm != nullptr);
     store_hit(rays, i, ray);
     if (ray.dist != kNoHit) atomicAdd(&counts[ray.tri], 1);
 }
@@ -735,7 +739,7 @@ __global__ void __launch_bounds__(256) k_reset(double* __restrict__ photonMap, d
 }
 
 // ---- on-device self-test of the shared-reciprocal division -----------------------------------
-// Draws (a, o, d) with the magnitudes ray_is_tame() admits and counts quotients that differ from
+// Draws (n, d) with the magnitudes ray_is_tame() admits (n down to 2^-100: denormal residuals) and counts quotients that differ from
 // __fdiv_rn.  out[0] = samples, out[1] = mismatches of one-step, out[2] = mismatches of two-step.
 __global__ void __launch_bounds__(256) k_selftest_division(unsigned long long* __restrict__ out, int iters, uint32_t salt)
 {
@@ -743,7 +747,7 @@ __global__ void __launch_bounds__(256) k_selftest_division(unsigned long long* _
     unsigned long long bad1 = 0, bad2 = 0;
     for (int it = 0; it < iters; it++) {
         uint32_t md = random_int(s) & 0x7fffffu, mn = random_int(s) & 0x7fffffu, e = random_int(s);
-        int ed = -(int)(e % 31u), en = -43 + (int)((e >> 8) % 49u);
+        int ed = -(int)(e % 31u), en = -100 + (int)((e >> 8) % 121u);
         if ((e >> 20) & 1u) md = ((e >> 21) & 1u) ? 0x7fffffu - (md & 0xffu) : (md & 0xffu);
         if ((e >> 22) & 1u) mn = ((e >> 23) & 1u) ? 0x7fffffu - (mn & 0xffu) : (mn & 0xffu);
         float d = __uint_as_float(((uint32_t)(ed + 127) << 23) | md | (((e >> 30) & 1u) << 31));

@@ -62,9 +62,10 @@ static int64_t inv_mod(int64_t x, int64_t m)
 
 static int check(int64_t a, int64_t b, unsigned long long* tested)
 {
-    static const int ex[4][2] = {{0, 0}, {-43, 0}, {5, -30}, {-20, -17}};
+    /* exponent pairs (n, d): includes the smallest numerators the kernel admits (denormal residuals) */
+    static const int ex[6][2] = {{0, 0}, {-43, 0}, {5, -30}, {-20, -17}, {-100, 0}, {-100, -30}};
     int bad = 0;
-    for (int e = 0; e < 4; e++)
+    for (int e = 0; e < 6; e++)
         for (int s = 0; s < 4; s++) {
             float n = ldexpf((float)a, ex[e][0] - 23), d = ldexpf((float)b, ex[e][1] - 23);
             if (s & 1) n = -n;
@@ -130,7 +131,7 @@ int main(int argc, char** argv)
             s ^= s << 13; s ^= s >> 17; s ^= s << 5; uint32_t md = s & 0x7fffff;
             s ^= s << 13; s ^= s >> 17; s ^= s << 5; uint32_t mn = s & 0x7fffff;
             s ^= s << 13; s ^= s >> 17; s ^= s << 5; uint32_t e = s;
-            int ed = -(int)(e % 31), en = -43 + (int)((e >> 8) % 64);
+            int ed = -(int)(e % 31), en = -100 + (int)((e >> 8) % 121);
             if ((e >> 20) & 1) md = ((e >> 21) & 1) ? 0x7fffff - (md & 0xff) : (md & 0xff);
             if ((e >> 22) & 1) mn = ((e >> 23) & 1) ? 0x7fffff - (mn & 0xff) : (mn & 0xff);
             uint32_t du = ((uint32_t)(ed + 127) << 23) | md | (((e >> 30) & 1) << 31);

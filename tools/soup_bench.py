@@ -1,0 +1,82 @@
+"""Incoherent-traversal stress (BASELINE.json config 5): synthetic triangle soup, ray sweep.
+
+    python tools/soup_bench.py --tris 1000000 --rays 1000000,10000000 [--check]
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+uv = importlib.import_module("small-project-uv-robot-ray-tracer_b200")
+from soup import make_soup, soup_route  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tris", type=int, default=1_000_000)
+    ap.add_argument("--size", type=float, default=0.01)
+    ap.add_argument("--rays", default="1000000")
+    ap.add_argument("--check", action="store_true", help="compare one launch with the oracle (CPU)")
+    args = ap.parse_args()
+    t0 = time.perf_counter()
+    tris = make_soup(args.tris, args.size)
+    t1 = time.perf_counter()
+    sim = uv.Sim(asset_root=os.path.join(ROOT, "data"))
+    sim.set_triangles(tris)
+    t2 = time.perf_counter()
+    sim.set_positions(soup_route())
+    sim.set_params(lightHeight=0.5, lightLength=1.0, lightIntensity=100.0, maxIterations=1, photonCount=1 << 20)
+    sim.init(None)
+    ctx = sim.ctx
+    info = ctx.scene_info()
+    print(json.dumps({"tris": args.tris, "make_s": round(t1 - t0, 2), "bvh_build_s": round(t2 - t1, 2), "scene": info,
+                      "floor": float(sim.mesh_info()["floor"]), "tame": ctx.get_option("scene_tame")}), flush=True)
+    floor = sim.mesh_info()["floor"]
+    pos = sim.positions
+    for P in [int(x) for x in args.rays.split(",")]:
+        lp = (np.float32(pos[5, 0]), np.float32(np.float32(floor) + np.float32(0.5)), np.float32(pos[5, 1]))
+        for binned in (0, 1):
+            ctx.set_option("bin_rays", binned)
+            times = []
+            for r in range(4):
+                ctx.reset(False)
+                ctx.mark(0)
+                ctx.trace_counts(lp, 1.0, 0, P, 0)
+                ctx.mark(1)
+                times.append(ctx.elapsed_ms(0, 1))
+            counts = ctx.read(uv.BUF.COUNTS)
+            best = min(times[1:])
+            print(json.dumps({"rays": P, "bin_rays": binned, "ms": round(best, 3), "mrays_s": round(P / best / 1e3, 1),
+                              "hits": int(counts.sum())}), flush=True)
+        if args.check:
+            import uvrt_testlib as T
+            t, nodes, tri_idx = sim.mesh_data()
+            n = min(P, 200_000)
+            O = T.oracle()
+            rays = np.zeros(n, dtype=T.RAY_DT)
+            O.orc_generate(T.ptr(rays), 0, n, lp[0], lp[1], lp[2], 1.0, 0, None)
+            temp = np.zeros(t.shape[0], dtype=np.int32)
+            cnt = T.Counters()
+            tc = time.perf_counter()
+            O.orc_extend(T.ptr(temp), T.ptr(t), T.ptr(rays), T.ptr(nodes), T.ptr(tri_idx), n, 0, C.byref(cnt))
+            tc = time.perf_counter() - tc
+            ctx.reset(False)
+            ctx.trace_counts(lp, 1.0, 0, n, 0)
+            got = ctx.read(uv.BUF.RAYS, n)
+            ok = got.tobytes() == rays.tobytes() and np.array_equal(ctx.read(uv.BUF.COUNTS), temp)
+            print(json.dumps({"check_rays": n, "bit_identical_to_oracle": bool(ok), "oracle_mrays_s": round(n / tc / 1e6, 3),
+                              "inner_visits_per_ray": round(cnt.innerVisits / n, 2), "tri_tests_per_ray": round(cnt.triTests / n, 2),
+                              "max_stack": int(cnt.maxStack)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
