@@ -271,9 +271,11 @@ def main():
             ctx.flush_l2()                       # cold L2 at the start of every step
             ctx.mark(0)
             for _ in range(n_gpus):              # n_gpus passes over the route, dealt out launch by launch
-                sim.tick()                       # host returns after its own stream sync (the reference's clFinish)
-            if s == k_steps - 1:
-                sim.reduce()                     # the run's one all-reduce (no-op on 1 GPU)
+                sim.compute_dosage_map()         # RayTracer::ComputeDosageMap: asynchronous, like Kernel::Run
+                if n_gpus == 1:
+                    sim.shade()                  # one GPU: shade after every pass, as MyApp::Tick does
+            if s == k_steps - 1 and n_gpus > 1:
+                sim.reduce()                     # the run's one all-reduce
                 sim.shade()
             ctx.mark(1)
             total_ms += ctx.elapsed_ms(0, 1)
@@ -313,12 +315,11 @@ def main():
         ctx.upload_scene(tris_h, nodes_h, idx_h)         # host arrays -> pinned staging -> device
         sim.set_params(maxIterations=n_gpus)
         sim.reset_dosage_map()
-        fin = False
-        while not fin:
-            fin = sim.tick()
-        sim.reduce()
+        for _ in range(n_gpus):
+            sim.compute_dosage_map()
+        sim.reduce()                                     # no-op on one GPU
         sim.shade()
-        return sim.read_dose()                           # device -> host
+        return sim.read_dose()                           # device -> host (synchronises)
 
     e2e_step()
     barrier()

@@ -106,6 +106,8 @@ struct uvrt_ctx {
     int nPairs = 0, nLeaves = 0, depth = 0;
     uint32_t rootRef = 0;
     int sceneTame = 0;
+    cudaTextureObject_t pairsTex = 0;   // the same buffer as a 1-D float4 texture ("fetch_mode" experiment)
+    int fetchMode = 0;
     float4* dPairs = nullptr;   // nPairs x 4 float4
     float4* dWtris = nullptr;   // nTris  x 4 float4 (leaf order: v0+tag, edge1, edge2, pad)
     float4* dVerts = nullptr;   // nTris  x 4 float4 (reference order and layout)
@@ -289,6 +291,13 @@ void launch_simple(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     }
 }
 
+template <int FETCH>
+void launch_simple_tex(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
+{
+    k_extend_simple<DIV_MARKSTEIN1, kStack, 128, 12, FETCH><<<grid_for(nRays, 128), 128, 0, ctx->stream>>>(
+        ctx->dCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm, ctx->pairsTex);
+}
+
 template <int DIV, int K, int HIST, int REFILL>
 void launch_persist_r(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
@@ -397,6 +406,8 @@ int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     int v = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
     if (v == 0) launch_simple<DIV_IEEE>(ctx, nRays, perm);
     else if (v == 1) launch_simple<DIV_MARKSTEIN2>(ctx, nRays, perm);
+    else if (v == 2 && ctx->fetchMode == 1 && ctx->pairsTex) launch_simple_tex<1>(ctx, nRays, perm);
+    else if (v == 2 && ctx->fetchMode == 2 && ctx->pairsTex) launch_simple_tex<2>(ctx, nRays, perm);
     else if (v == 2) launch_simple<DIV_MARKSTEIN1>(ctx, nRays, perm);
     else if (v >= 10 && v < 25) {
         int k = (v - 10) / 3, d = (v - 10) % 3;
@@ -494,6 +505,7 @@ void uvrt_destroy(uvrt_ctx* ctx)
     }
     if (ctx->genStream) cudaStreamDestroy(ctx->genStream);
     if (ctx->hStage) cudaFreeHost(ctx->hStage);
+    if (ctx->pairsTex) cudaDestroyTextureObject(ctx->pairsTex);
     for (auto& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
     for (auto e : ctx->freeEvents) cudaEventDestroy(e);
     for (auto e : ctx->marks) if (e) cudaEventDestroy(e);
@@ -627,8 +639,19 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
     int rc;
     if (pairBytes > ctx->pairCap) {
         ctx->pairCap = 0;
+        if (ctx->pairsTex) { cudaDestroyTextureObject(ctx->pairsTex); ctx->pairsTex = 0; }
         if ((rc = dev_alloc(ctx, &ctx->dPairs, pairBytes / 16))) return rc;
         ctx->pairCap = pairBytes;
+        if (pairBytes / 16 <= (1u << 27)) {
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = ctx->dPairs;
+            rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+            rd.res.linear.sizeInBytes = pairBytes;
+            cudaTextureDesc td{};
+            td.readMode = cudaReadModeElementType;
+            if (cudaCreateTextureObject(&ctx->pairsTex, &rd, &td, nullptr) != cudaSuccess) { ctx->pairsTex = 0; cudaGetLastError(); }
+        }
     }
     if (wtriBytes > ctx->wtriCap) {
         ctx->wtriCap = 0;
@@ -973,6 +996,7 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
     else if (!strcmp(key, "refill")) ctx->refill = value;
     else if (!strcmp(key, "simple_cfg")) ctx->simpleCfg = value;
     else if (!strcmp(key, "pipeline")) ctx->pipeline = value;
+    else if (!strcmp(key, "fetch_mode")) ctx->fetchMode = value;
     else if (!strncmp(key, "bin_", 4)) {
         if (!strcmp(key, "bin_rays")) ctx->binRays = value;
         else if (!strcmp(key, "bin_y") && value >= 1 && value <= 64) ctx->binY = value;
@@ -1001,6 +1025,7 @@ int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value)
     else if (!strcmp(key, "refill")) *value = ctx->refill;
     else if (!strcmp(key, "simple_cfg")) *value = ctx->simpleCfg;
     else if (!strcmp(key, "pipeline")) *value = ctx->pipeline;
+    else if (!strcmp(key, "fetch_mode")) *value = ctx->fetchMode;
     else if (!strcmp(key, "bin_rays")) *value = ctx->binRays;
     else if (!strcmp(key, "bin_y")) *value = ctx->binY;
     else if (!strcmp(key, "bin_t")) *value = ctx->binT;

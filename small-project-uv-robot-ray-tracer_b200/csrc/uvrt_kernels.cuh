@@ -422,9 +422,20 @@ __device__ __forceinline__ bool ray_is_tame(const RayCtx& r)
 // reference's.  `pairs` holds, per inner node, its two children's boxes and references
 // (2 x 32 bytes, see intersect_aabb); `wtris` holds leaf triangles in leaf order (4 x float4:
 // v0+tag, edge1, edge2, pad -- two 32-byte sectors).
-template <int DIV, int STACK, int OCT>
+// Node fetch path (experiment, "fetch_mode"): 0 = two LDG.256 through the LSU; 1 = four 16-byte
+// texture fetches; 2 = first child through the LSU, second through the texture unit.
+__device__ __forceinline__ W4 tex_w4(cudaTextureObject_t tex, uint32_t texel)
+{
+    float4 a = tex1Dfetch<float4>(tex, (int)texel), b = tex1Dfetch<float4>(tex, (int)texel + 1);
+    W4 r;
+    r.w0 = pk2(a.x, a.y); r.w1 = pk2(a.z, a.w); r.w2 = pk2(b.x, b.y); r.w3 = pk2(b.z, b.w);
+    return r;
+}
+
+template <int DIV, int STACK, int OCT, int FETCH = 0>
 __device__ __forceinline__ void bvh_intersect(RayCtx& ray, const float4* __restrict__ pairs,
-                                              const float4* __restrict__ wtris, uint32_t rootRef)
+                                              const float4* __restrict__ wtris, uint32_t rootRef,
+                                              cudaTextureObject_t tex = 0)
 {
     uint32_t stack[STACK];
     int sp = 0;
@@ -448,7 +459,10 @@ __device__ __forceinline__ void bvh_intersect(RayCtx& ray, const float4* __restr
             continue;
         }
         const float4* p = pairs + 4ull * cur;
-        W4 ca = ldg256w(p), cb = ldg256w(p + 2);
+        W4 ca, cb;
+        if (FETCH == 1) { ca = tex_w4(tex, cur * 4u); cb = tex_w4(tex, cur * 4u + 2u); }
+        else if (FETCH == 2) { ca = ldg256w(p); cb = tex_w4(tex, cur * 4u + 2u); }
+        else { ca = ldg256w(p); cb = ldg256w(p + 2); }
         float t1, t2;
         const bool h1 = intersect_aabb<DIV, OCT>(ray, ca, t1);
         const bool h2 = intersect_aabb<DIV, OCT>(ray, cb, t2);
@@ -464,9 +478,10 @@ __device__ __forceinline__ void bvh_intersect(RayCtx& ray, const float4* __restr
     }
 }
 
-template <int DIV, int STACK>
+template <int DIV, int STACK, int FETCH = 0>
 __device__ __forceinline__ void trace_one(RayCtx& ray, const float4* __restrict__ pairs,
-                                          const float4* __restrict__ wtris, uint32_t rootRef, bool sceneTame, bool binned)
+                                          const float4* __restrict__ wtris, uint32_t rootRef, bool sceneTame, bool binned,
+                                          cudaTextureObject_t tex = 0)
 {
     if (DIV == DIV_IEEE) {
         bvh_intersect<DIV_IEEE, STACK, -1>(ray, pairs, wtris, rootRef);
@@ -478,15 +493,15 @@ __device__ __forceinline__ void trace_one(RayCtx& ray, const float4* __restrict_
             // eight loops in every warp: they take the generic loop (-1).
             const int oct = !binned ? -1 : (ray.dx < 0.0f ? 1 : 0) | (ray.dy < 0.0f ? 2 : 0) | (ray.dz < 0.0f ? 4 : 0);
             switch (oct) {
-            case -1: bvh_intersect<DIV, STACK, -1>(ray, pairs, wtris, rootRef); break;
-            case 0: bvh_intersect<DIV, STACK, 0>(ray, pairs, wtris, rootRef); break;
-            case 1: bvh_intersect<DIV, STACK, 1>(ray, pairs, wtris, rootRef); break;
-            case 2: bvh_intersect<DIV, STACK, 2>(ray, pairs, wtris, rootRef); break;
-            case 3: bvh_intersect<DIV, STACK, 3>(ray, pairs, wtris, rootRef); break;
-            case 4: bvh_intersect<DIV, STACK, 4>(ray, pairs, wtris, rootRef); break;
-            case 5: bvh_intersect<DIV, STACK, 5>(ray, pairs, wtris, rootRef); break;
-            case 6: bvh_intersect<DIV, STACK, 6>(ray, pairs, wtris, rootRef); break;
-            default: bvh_intersect<DIV, STACK, 7>(ray, pairs, wtris, rootRef); break;
+            case -1: bvh_intersect<DIV, STACK, -1, FETCH>(ray, pairs, wtris, rootRef, tex); break;
+            case 0: bvh_intersect<DIV, STACK, 0, FETCH>(ray, pairs, wtris, rootRef, tex); break;
+            case 1: bvh_intersect<DIV, STACK, 1, FETCH>(ray, pairs, wtris, rootRef, tex); break;
+            case 2: bvh_intersect<DIV, STACK, 2, FETCH>(ray, pairs, wtris, rootRef, tex); break;
+            case 3: bvh_intersect<DIV, STACK, 3, FETCH>(ray, pairs, wtris, rootRef, tex); break;
+            case 4: bvh_intersect<DIV, STACK, 4, FETCH>(ray, pairs, wtris, rootRef, tex); break;
+            case 5: bvh_intersect<DIV, STACK, 5, FETCH>(ray, pairs, wtris, rootRef, tex); break;
+            case 6: bvh_intersect<DIV, STACK, 6, FETCH>(ray, pairs, wtris, rootRef, tex); break;
+            default: bvh_intersect<DIV, STACK, 7, FETCH>(ray, pairs, wtris, rootRef, tex); break;
             }
         } else {
             bvh_intersect<DIV_IEEE, STACK, -1>(ray, pairs, wtris, rootRef);
@@ -513,18 +528,18 @@ __device__ __forceinline__ void store_hit(float4* __restrict__ rays, long long i
 }
 
 // Variant A: one thread per ray, the literal control flow of extend.cl:85-99.
-template <int DIV, int STACK, int THREADS, int MINBLOCKS>
+template <int DIV, int STACK, int THREADS, int MINBLOCKS, int FETCH = 0>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_extend_simple(int* __restrict__ counts, const float4* __restrict__ wtris,
                                                        float4* __restrict__ rays, const float4* __restrict__ pairs,
                                                        uint32_t rootRef, long long nRays, int sceneTame,
-                                                       const uint32_t* __restrict__ perm)
+                                                       const uint32_t* __restrict__ perm, cudaTextureObject_t tex = 0)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nRays) return;
     if (perm) i = perm[i];
     RayCtx ray;
     load_ray(rays, i, ray);
-    trace_one<DIV, STACK>(ray, pairs, wtris, rootRef, sceneTame != 0, perm != nullptr);
+    trace_one<DIV, STACK, FETCH>(ray, pairs, wtris, rootRef, sceneTame != 0, perm != nullptr, tex);
     store_hit(rays, i, ray);
     if (ray.dist != kNoHit) atomicAdd(&counts[ray.tri], 1);
 }

@@ -1,10 +1,14 @@
-"""Times every extend variant on one launch of the default route (2,796,202 rays, lange_route
-position 0 on testroomopt) with CUDA events on the context's stream.  Run on the GPU box:
+"""Times extend variants on one launch of the default route (2,796,202 rays, lange_route position 0
+on testroomopt) with CUDA events on the context's stream.  Run on the GPU box:
 
-    python tools/variant_sweep.py [--rays N] [--reps R] [--variants 0,1,2,...]
+    python tools/variant_sweep.py [--rays N] [--reps R] [--variants 0,1,2,...] [--bin "0;16,32,128"]
+
+The timed region is uvrt_extend: (bin scan + scatter when binning is on) + the extend kernel.
+Every configuration's per-triangle counts are compared with the first one's.
 """
 import argparse
 import importlib
+import itertools
 import json
 import os
 import sys
@@ -26,7 +30,8 @@ def part1by1(x):
 
 
 def sorted_rays(gen, spec, lp, length):
-    """Orders rays by (direction cell, origin slice): equal-probability cells in (dir.y, azimuth)."""
+    """Host-side ray orderings (to explore what re-ordering can buy): equal-probability cells in
+    (dir.y, azimuth) x origin slices.  spec = "none" or "nT,nP,nY[,mode]"."""
     if spec == "none":
         return gen
     parts = spec.split(",")
@@ -37,14 +42,12 @@ def sorted_rays(gen, spec, lp, length):
     ph = np.clip(((np.arctan2(d[:, 2], d[:, 0]) + np.pi) / (2 * np.pi) * nP).astype(np.int64), 0, nP - 1)
     y = np.clip(((o[:, 1] - lp[1]) / length * nY).astype(np.int64), 0, nY - 1)
     if mode == "morton":
-        cell = (part1by1(t) | (part1by1(ph) << 1)).astype(np.int64)
-        key = cell * nY + y
+        key = (part1by1(t) | (part1by1(ph) << 1)).astype(np.int64) * nY + y
     elif mode == "ytp":
         key = (y * nT + t) * nP + ph
-    elif mode == "ytps":      # serpentine azimuth: neighbouring bins stay neighbours across rows
-        phs = np.where(t % 2 == 0, ph, nP - 1 - ph)
-        key = (y * nT + t) * nP + phs
-    elif mode == "morton3":   # interleave y, t, ph (equal bit counts expected)
+    elif mode == "ytps":      # serpentine azimuth
+        key = (y * nT + t) * nP + np.where(t % 2 == 0, ph, nP - 1 - ph)
+    elif mode == "morton3":
         def p3(x):
             x = x.astype(np.uint64) & 0x3ff
             x = (x | (x << 16)) & 0x30000ff
@@ -53,81 +56,87 @@ def sorted_rays(gen, spec, lp, length):
             x = (x | (x << 2)) & 0x9249249
             return x
         key = (p3(t) | (p3(ph) << 1) | (p3(y) << 2)).astype(np.int64)
-    elif mode == "tyq":       # direction cell major, then origin slice (fine), then azimuth
+    elif mode == "tyq":       # dir.y cell, then origin slice, then azimuth (what the device binning uses)
         key = (t * nY + y) * nP + ph
     else:
         key = (t * nP + ph) * nY + y
     return gen[np.argsort(key, kind="stable")]
 
 
+def ints(s):
+    return [int(x) for x in s.split(",")]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=2796202)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--variants", default="0,1,2,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24")
-    ap.add_argument("--hist", default="0,1")
-    ap.add_argument("--bps", default="0")
-    ap.add_argument("--refill", default="24")
-    ap.add_argument("--cfg", default="0", help="simple_cfg values (block size / register cap of the simple kernel)")
+    ap.add_argument("--variants", default="0,1,2")
+    ap.add_argument("--hist", default="0", help="hist_mode values (persistent variants only)")
+    ap.add_argument("--refill", default="24", help="refill thresholds (persistent variants only)")
+    ap.add_argument("--cfg", default="1", help="simple_cfg values (one-thread-per-ray variants only)")
+    ap.add_argument("--fetch", default="0", help="fetch_mode values: 0 LSU, 1 texture, 2 mixed (variant 2 only)")
+    ap.add_argument("--bin", default="16,32,128", help="device binning: 0 (off) or nY,nT,nP; ';'-separated")
+    ap.add_argument("--sort", default="none", help="host-side orderings, ';'-separated (see sorted_rays)")
     ap.add_argument("--positions", default="0")
-    ap.add_argument("--bin", default="0", help="device binning configs: 0 (off) or nY,nT,nP; ';'-separated")
-    ap.add_argument("--sort", default="none", help="host-side ray orderings to try: none or nT,nP,nY[,morton]; ';'-separated")
     args = ap.parse_args()
+
     sim = uv.Sim(asset_root=os.path.join(ROOT, "data"))
     sim.load_mesh("testroomopt")
     sim.init("lange_route")
     c = sim.ctx
     floor = sim.mesh_info()["floor"]
-    p = sim.params
-    pos = sim.positions
+    p, pos, P = sim.params, sim.positions, args.rays
     print(json.dumps({"device": c.device_info(), "scene": c.scene_info()}))
-    P = args.rays
-    for pi in [int(x) for x in args.positions.split(",")]:
+    for pi in ints(args.positions):
         lp = (np.float32(pos[pi, 0]), np.float32(np.float32(floor) + np.float32(p.lightHeight)), np.float32(pos[pi, 1]))
         c.generate(lp, p.lightLength, 0, P, 0)
-        gen = c.read(uv.BUF.RAYS, P)
+        gen0 = c.read(uv.BUF.RAYS, P)
         ref_counts = None
-        gen0 = gen
-        for sort in args.sort.split(";"):
-          gen = sorted_rays(gen0, sort, lp, p.lightLength)
-          for binspec in args.bin.split(";"):
-           if binspec == "0":
-               c.set_option("bin_rays", 0)
-           else:
-               by, bt, bp = [int(x) for x in binspec.split(",")]
-               c.set_option("bin_rays", 1); c.set_option("bin_y", by); c.set_option("bin_t", bt); c.set_option("bin_p", bp)
-           for v in [int(x) for x in args.variants.split(",")]:
-               for hist in [int(x) for x in args.hist.split(",")]:
-                   if hist and v < 10:
-                       continue
-                   for bps, refill in [(int(x), int(y)) for x in args.bps.split(",") for y in (args.refill.split(",") if v >= 10 else args.cfg.split(","))]:
-                       c.set_option("refill" if v >= 10 else "simple_cfg", refill)
-                       c.set_option("extend_variant", v)
-                       c.set_option("hist_mode", hist)
-                       c.set_option("blocks_per_sm", bps)
-                       times = []
-                       for r in range(args.reps + 2):
-                           c.reset(False)
-                           if sort == "none":
-                               c.generate(lp, p.lightLength, 0, P, 0)
-                           else:
-                               c.write(uv.BUF.RAYS, gen)
-                           c.mark(0)
-                           c.extend(P)
-                           c.mark(1)
-                           t = c.elapsed_ms(0, 1)
-                           if r >= 2:
-                               times.append(t)
-                       counts = c.read(uv.BUF.COUNTS)
-                       if ref_counts is None:
-                           ref_counts = counts
-                       ok = bool(np.array_equal(counts, ref_counts))
-                       best = min(times)
-                       print(json.dumps({"pos": pi, "sort": sort, "bin": binspec, "variant": v, "hist": hist, "bps": bps, "refill_or_cfg": refill, "ms_best": round(best, 4),
-                                         "ms_med": round(float(np.median(times)), 4), "mrays_s": round(P / best / 1e3, 1),
-                                         "counts_equal": ok}), flush=True)
-    c.set_option("extend_variant", -1)
-    c.set_option("bin_rays", 1)
+        for sort, binspec, v in itertools.product(args.sort.split(";"), args.bin.split(";"), ints(args.variants)):
+            gen = sorted_rays(gen0, sort, lp, p.lightLength)
+            if binspec == "0":
+                c.set_option("bin_rays", 0)
+            else:
+                by, bt, bp = ints(binspec)
+                c.set_option("bin_rays", 1)
+                c.set_option("bin_y", by)
+                c.set_option("bin_t", bt)
+                c.set_option("bin_p", bp)
+            persistent = v >= 10
+            knobs = itertools.product(ints(args.hist) if persistent else [0],
+                                      ints(args.refill) if persistent else [24],
+                                      [1] if persistent else ints(args.cfg),
+                                      ints(args.fetch) if v == 2 else [0])
+            for hist, refill, cfg, fetch in knobs:
+                c.set_option("extend_variant", v)
+                c.set_option("hist_mode", hist)
+                c.set_option("refill", refill)
+                c.set_option("simple_cfg", cfg)
+                c.set_option("fetch_mode", fetch)
+                times = []
+                for r in range(args.reps + 2):
+                    c.reset(False)
+                    if sort == "none":
+                        c.generate(lp, p.lightLength, 0, P, 0)
+                    else:
+                        c.write(uv.BUF.RAYS, gen)
+                    c.mark(0)
+                    c.extend(P)
+                    c.mark(1)
+                    t = c.elapsed_ms(0, 1)
+                    if r >= 2:
+                        times.append(t)
+                counts = c.read(uv.BUF.COUNTS)
+                if ref_counts is None:
+                    ref_counts = counts
+                best = min(times)
+                print(json.dumps({"pos": pi, "sort": sort, "bin": binspec, "variant": v, "hist": hist, "refill": refill,
+                                  "cfg": cfg, "fetch": fetch, "ms_best": round(best, 4),
+                                  "ms_med": round(float(np.median(times)), 4), "mrays_s": round(P / best / 1e3, 1),
+                                  "counts_equal": bool(np.array_equal(counts, ref_counts))}), flush=True)
+    for k, v in (("extend_variant", -1), ("bin_rays", 1), ("hist_mode", 0), ("fetch_mode", 0), ("simple_cfg", 1), ("refill", 24)):
+        c.set_option(k, v)
 
 
 if __name__ == "__main__":
