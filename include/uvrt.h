@@ -82,6 +82,14 @@ int uvrt_device_info(uvrt_ctx* ctx, char* dst, size_t bytes, int* smCount, int* 
 int uvrt_upload_scene(uvrt_ctx* ctx, const void* tris, int nTris, const void* nodes, int nNodes,
                       const uint32_t* triIdx);
 
+/* BVH::Build (bvh.cpp:13-44) on the device: binned-SAH BVH2 with the reference builder's tree, node
+ * numbering and triIdx order (bit-identical to host/bvh.cpp).  tris: nTris x 64 B (host); the
+ * centroid lanes are written back when trisOut != NULL (the builder computes them, bvh.cpp:23).
+ * nodesOut: nodeCapacity x 32 B (host; 2*nTris + 64 is always enough); triIdxOut: nTris x u32.
+ * *nodesUsed = highest used node index + 1.  Synchronises.  Independent of the uploaded scene. */
+int uvrt_build_bvh(uvrt_ctx* ctx, const void* tris, int nTris, void* nodesOut, int nodeCapacity,
+                   uint32_t* triIdxOut, uint32_t* nodesUsed, void* trisOut);
+
 /* ---- stages ---------------------------------------------------------------------------- */
 /* reset.cl:4-26 via RayTracer::ClearBuffers (raytracer.cpp:133-143) */
 int uvrt_reset(uvrt_ctx* ctx, int resetColor);

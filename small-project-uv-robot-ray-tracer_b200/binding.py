@@ -86,6 +86,7 @@ def lib():
         "uvrt_last_error": (C.c_char_p, [vp]),
         "uvrt_device_info": (i, [vp, C.c_char_p, C.c_size_t, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
         "uvrt_upload_scene": (i, [vp, vp, i, vp, i, vp]),
+        "uvrt_build_bvh": (i, [vp, vp, i, vp, i, vp, C.POINTER(u32), vp]),
         "uvrt_reset": (i, [vp, i]),
         "uvrt_generate": (i, [vp, f, f, f, f, i64, i64, u32]),
         "uvrt_extend": (i, [vp, i64]),
@@ -137,6 +138,7 @@ def host():
         "uvrt_sim_last_error": (C.c_char_p, [vp]),
         "uvrt_sim_load_mesh": (i, [vp, C.c_char_p]),
         "uvrt_sim_set_triangles": (i, [vp, vp, i]),
+        "uvrt_sim_set_device_bvh": (i, [vp, i]),
         "uvrt_sim_mesh_info": (i, [vp, C.POINTER(i), C.POINTER(f), C.POINTER(C.c_uint)]),
         "uvrt_sim_mesh_data": (i, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "uvrt_sim_load_route": (i, [vp, C.c_char_p]),
@@ -216,6 +218,18 @@ class Context:
         n_nodes = nodes.nbytes // 32
         self.check(self.L.uvrt_upload_scene(self.h, _p(tris), tris.shape[0], _p(nodes), n_nodes, _p(tri_idx)))
         self.n_tris = tris.shape[0]
+
+    def build_bvh(self, tris):
+        """Device BVH build. Returns (tris with centroids, nodes, triIdx) like binding.build_bvh()."""
+        t = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 16)
+        n = t.shape[0]
+        cap = 2 * n + 64
+        nodes = np.zeros(cap, dtype=NODE_DTYPE)
+        tri_idx = np.zeros(n, dtype=np.uint32)
+        out_tris = np.zeros_like(t)
+        used = C.c_uint32()
+        self.check(self.L.uvrt_build_bvh(self.h, _p(t), n, _p(nodes), cap, _p(tri_idx), C.byref(used), _p(out_tris)))
+        return out_tris, nodes[: used.value], tri_idx
 
     def scene_info(self):
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
@@ -359,6 +373,9 @@ class Sim:
 
     def load_mesh(self, model_file):
         self.check(self.H.uvrt_sim_load_mesh(self.h, model_file.encode()))
+
+    def set_device_bvh(self, on=True):
+        self.check(self.H.uvrt_sim_set_device_bvh(self.h, int(on)))
 
     def set_triangles(self, tris):
         tris = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 16)

@@ -1,0 +1,577 @@
+// uvrt_bvh_build.cuh -- binned-SAH BVH2 build on the device, producing the SAME tree, node numbering
+// and triIdx order as the host builder (host/bvh.cpp) and therefore as the reference's
+// /root/reference/bvh.cpp:13-220.  SURVEY.md section 8(f)-1: the CPU builder is the next wall after
+// the wavefront path (0.1 s for the room, 6.4 s for the 10 M-triangle soup on 16 cores).
+//
+// What has to be reproduced exactly, and how it is done in parallel:
+//   * split selection: per node and axis, 8 bins of triangle counts and vertex bounds (min/max are
+//     exact and order-free, so shared-memory atomics give the same bins); the sweep over the 7 planes
+//     is run by one thread with the host's fp32 expressions in the host's order (no FMA), including the
+//     reference's lagging right-hand box (bvh.cpp:134-138).
+//   * the in-place partition `while (i <= j) if (left(A[i])) i++; else swap(A[i], A[j--]);` leaves a
+//     specific, unstable order.  Its result has a closed form (checked against the sequential loop on
+//     2e5 random inputs, tests/test_host.py): with L = number of "left" elements,
+//       - left elements of the prefix [0, L) stay;
+//       - the k-th "hole" of the prefix (right element, from the left) receives the k-th left element
+//         of the suffix counted from the right end;
+//       - hole k's own element moves to `last` (k = 1) or to one slot before the (k-1)-th suffix-left;
+//       - every right element of the suffix moves one slot towards the front, except the suffix's
+//         first element, which (if right) moves to one slot before the last suffix-left (or to `last`).
+//     Ranks come from block-wide prefix sums, so each element finds its destination independently.
+//   * node numbering: children are allocated as an adjacent pair when a node splits, the left
+//     subtree's descendants before the right's; the first four levels are numbered from slot 2 and
+//     each level-4 subtree ("job") owns [base_i, base_i + 2*tris_i) (bvh.cpp:31-42).  The device build
+//     numbers nodes arbitrarily (atomic counter), then computes subtree slot counts bottom-up and the
+//     reference indices top-down, level by level.
+// One thread block per active node and level (one thread for nodes of at most 16 triangles); leaves
+// copy their segment to the final index array.  Known limit: the top levels of a very large mesh are
+// processed by a single block each (10 M triangles: 0.34 of 0.72 s); splitting those nodes over several
+// blocks is the next step.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace uvrt_bvh {
+
+constexpr int kBins = 8;
+constexpr int kThreads = 256;
+
+struct BNode {            // 64 bytes, temporary numbering
+    float bmin[3]; uint32_t first;
+    float bmax[3]; uint32_t count;
+    float cmin[3]; uint32_t left;     // temp index of the left child (right = left + 1); 0 = leaf
+    float cmax[3]; uint32_t depth;
+};
+
+struct BAux {             // renumbering state per node
+    uint32_t sFull;       // slots allocated inside Subdivide(node) when numbered recursively
+    uint32_t alloc;       // value of the allocation pointer when Subdivide(node) starts
+    uint32_t ref;         // index in the reference numbering
+    uint32_t pad;
+};
+
+__device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
+
+// order-preserving float <-> uint (for atomicMin / atomicMax on floats)
+__device__ __forceinline__ uint32_t enc(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec(uint32_t u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ float half_area(const float* lo, const float* hi)
+{
+    float ex = fs(hi[0], lo[0]), ey = fs(hi[1], lo[1]), ez = fs(hi[2], lo[2]);
+    return fa(fa(fm(ex, ey), fm(ey, ez)), fm(ez, ex));
+}
+
+__device__ __forceinline__ int bin_of(float c, float lo, float scale)
+{
+    int b = (int)fm(fs(c, lo), scale);
+    return b < kBins - 1 ? b : kBins - 1;
+}
+
+// centroid = (v0 + v1 + v2) * 0.3333f (bvh.cpp:23); also initialises the identity index array
+__global__ void __launch_bounds__(256) k_centroids(float4* __restrict__ tris, uint32_t* __restrict__ idx, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = tris[4ull * i], b = tris[4ull * i + 1], c = tris[4ull * i + 2];
+    float4 ce = tris[4ull * i + 3];
+    ce.x = fm(fa(fa(a.x, b.x), c.x), 0.3333f);
+    ce.y = fm(fa(fa(a.y, b.y), c.y), 0.3333f);
+    ce.z = fm(fa(fa(a.z, b.z), c.z), 0.3333f);
+    tris[4ull * i + 3] = ce;
+    idx[i] = (uint32_t)i;
+}
+
+// block-wide helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warpSums, uint32_t& total)
+{
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += n;
+    }
+    __syncthreads();                       // warpSums may still be read from a previous call
+    if (lane == 31) warpSums[w] = inc;
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; k++) {
+        uint32_t s = warpSums[k];
+        before += (k < (int)w) ? s : 0u;
+        tot += s;
+    }
+    total = tot;
+    return before + inc - v;
+}
+
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { float n = __shfl_xor_sync(0xffffffffu, v, o); v = n < v ? n : v; }
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { float n = __shfl_xor_sync(0xffffffffu, v, o); v = n > v ? n : v; }
+    return v;
+}
+
+// Root: bounds of all triangles and of their centroids (UpdateNodeBounds, bvh.cpp:181-220).
+__global__ void __launch_bounds__(256) k_root_bounds(const float4* __restrict__ tris, int n, uint32_t* __restrict__ acc /*12 encoded*/)
+{
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+    float clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 v[3] = {tris[4ull * i], tris[4ull * i + 1], tris[4ull * i + 2]};
+        float4 c = tris[4ull * i + 3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lo[0] = fminf(lo[0], v[k].x); hi[0] = fmaxf(hi[0], v[k].x);
+            lo[1] = fminf(lo[1], v[k].y); hi[1] = fmaxf(hi[1], v[k].y);
+            lo[2] = fminf(lo[2], v[k].z); hi[2] = fmaxf(hi[2], v[k].z);
+        }
+        clo[0] = fminf(clo[0], c.x); chi[0] = fmaxf(chi[0], c.x);
+        clo[1] = fminf(clo[1], c.y); chi[1] = fmaxf(chi[1], c.y);
+        clo[2] = fminf(clo[2], c.z); chi[2] = fmaxf(chi[2], c.z);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float a = warp_min(lo[k]), b = warp_max(hi[k]), c = warp_min(clo[k]), d = warp_max(chi[k]);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&acc[k], enc(a)); atomicMax(&acc[3 + k], enc(b));
+            atomicMin(&acc[6 + k], enc(c)); atomicMax(&acc[9 + k], enc(d));
+        }
+    }
+}
+
+__global__ void k_init_root(BNode* __restrict__ nodes, const uint32_t* __restrict__ acc, int n, uint32_t* __restrict__ levelList,
+                            uint32_t* __restrict__ counters /*[0]=next node id, [1],[2]=next-level list sizes*/)
+{
+    BNode r;
+    for (int k = 0; k < 3; k++) { r.bmin[k] = dec(acc[k]); r.bmax[k] = dec(acc[3 + k]); r.cmin[k] = dec(acc[6 + k]); r.cmax[k] = dec(acc[9 + k]); }
+    r.first = 0; r.count = (uint32_t)n; r.left = 0; r.depth = 0;
+    nodes[0] = r;
+    levelList[0] = 0;
+    counters[0] = 1;      // temp ids: root = 0, children pairs follow
+    counters[1] = 0;      // nodes queued for the next level: block-per-node list
+    counters[2] = 0;      //                                   thread-per-node list
+}
+
+// Children with at most kSmall triangles are finished by one thread each (k_level_small).
+constexpr uint32_t kSmall = 16;
+__device__ __forceinline__ void enqueue_child(uint32_t id, uint32_t count, uint32_t* __restrict__ nextBig,
+                                              uint32_t* __restrict__ nextSmall, uint32_t* __restrict__ counters)
+{
+    if (count > kSmall) nextBig[atomicAdd(&counters[1], 1u)] = id;
+    else nextSmall[atomicAdd(&counters[2], 1u)] = id;
+}
+
+// One level of the build: one block per active node with more than kSmall triangles.
+__global__ void __launch_bounds__(kThreads) k_level(const uint32_t* __restrict__ levelList, BNode* __restrict__ nodes,
+                                                    const float4* __restrict__ tris, const uint32_t* __restrict__ src,
+                                                    uint32_t* __restrict__ dst, uint32_t* __restrict__ finalIdx,
+                                                    uint32_t* __restrict__ rankScratch, uint32_t* __restrict__ holePos,
+                                                    uint32_t* __restrict__ sleftPos, uint32_t* __restrict__ nextBig,
+                                                    uint32_t* __restrict__ nextSmall, uint32_t* __restrict__ counters)
+{
+    __shared__ uint32_t sCnt[3][kBins];
+    __shared__ uint32_t sLo[3][kBins][3], sHi[3][kBins][3];
+    __shared__ uint32_t warpSums[kThreads / 32];
+    __shared__ float red[kThreads / 32][24];
+    __shared__ int sAxis, sPlane, sSplit;
+    __shared__ uint32_t sL, sChild;
+
+    const uint32_t nodeId = levelList[blockIdx.x];
+    const BNode nd = nodes[nodeId];
+    const uint32_t first = nd.first, count = nd.count;
+    const int tid = threadIdx.x;
+
+    // ---- 1. bins (bvh.cpp:108-129) ----
+    for (int k = tid; k < 3 * kBins; k += kThreads) {
+        (&sCnt[0][0])[k] = 0;
+        for (int c = 0; c < 3; c++) { (&sLo[0][0][0])[k * 3 + c] = 0xffffffffu; (&sHi[0][0][0])[k * 3 + c] = 0u; }
+    }
+    __syncthreads();
+    float scale[3];
+    bool axisOn[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        axisOn[a] = nd.cmin[a] != nd.cmax[a];
+        scale[a] = axisOn[a] ? __fdiv_rn(8.0f, fs(nd.cmax[a], nd.cmin[a])) : 0.0f;
+    }
+    for (uint32_t i = tid; i < count; i += kThreads) {
+        const uint32_t t = src[first + i];
+        const float4 v0 = __ldg(tris + 4ull * t), v1 = __ldg(tris + 4ull * t + 1), v2 = __ldg(tris + 4ull * t + 2), ce = __ldg(tris + 4ull * t + 3);
+        const float tlo[3] = {fminf(fminf(v0.x, v1.x), v2.x), fminf(fminf(v0.y, v1.y), v2.y), fminf(fminf(v0.z, v1.z), v2.z)};
+        const float thi[3] = {fmaxf(fmaxf(v0.x, v1.x), v2.x), fmaxf(fmaxf(v0.y, v1.y), v2.y), fmaxf(fmaxf(v0.z, v1.z), v2.z)};
+        const float c[3] = {ce.x, ce.y, ce.z};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (!axisOn[a]) continue;
+            const int b = bin_of(c[a], nd.cmin[a], scale[a]);
+            atomicAdd(&sCnt[a][b], 1u);
+#pragma unroll
+            for (int k = 0; k < 3; k++) { atomicMin(&sLo[a][b][k], enc(tlo[k])); atomicMax(&sHi[a][b][k], enc(thi[k])); }
+        }
+    }
+    __syncthreads();
+
+    // ---- 2. sweep and decision (bvh.cpp:130-150, 52-54, 64-66), one thread, host arithmetic ----
+    if (tid == 0) {
+        float best = 1e30f;
+        int axis = 0, plane = 0;
+        for (int a = 0; a < 3; a++) {
+            if (!axisOn[a]) continue;
+            float binLo[kBins][3], binHi[kBins][3];
+            for (int b = 0; b < kBins; b++)
+                for (int k = 0; k < 3; k++) {
+                    // an empty bin keeps the builder's +-1e30 sentinels
+                    binLo[b][k] = sCnt[a][b] ? dec(sLo[a][b][k]) : 1e30f;
+                    binHi[b][k] = sCnt[a][b] ? dec(sHi[a][b][k]) : -1e30f;
+                }
+            float costL[kBins - 1], costR[kBins - 1];
+            float lLo[3] = {1e30f, 1e30f, 1e30f}, lHi[3] = {-1e30f, -1e30f, -1e30f};
+            float rLo[3] = {1e30f, 1e30f, 1e30f}, rHi[3] = {-1e30f, -1e30f, -1e30f};
+            int nL = 0, nR = 0;
+            for (int i = 0; i < kBins - 1; i++) {
+                nL += (int)sCnt[a][i];
+                for (int k = 0; k < 3; k++) {
+                    lLo[k] = binLo[i][k] < lLo[k] ? binLo[i][k] : lLo[k];
+                    lHi[k] = binHi[i][k] > lHi[k] ? binHi[i][k] : lHi[k];
+                }
+                costL[i] = fm(__int2float_rn(nL), half_area(lLo, lHi));
+                const int rb = kBins - 2 - i;         // box index lags the count index by one
+                nR += (int)sCnt[a][rb + 1];
+                for (int k = 0; k < 3; k++) {
+                    rLo[k] = binLo[rb][k] < rLo[k] ? binLo[rb][k] : rLo[k];
+                    rHi[k] = binHi[rb][k] > rHi[k] ? binHi[rb][k] : rHi[k];
+                }
+                costR[rb] = fm(__int2float_rn(nR), half_area(rLo, rHi));
+            }
+            for (int i = 0; i < kBins - 1; i++) {
+                const float c = fa(costL[i], costR[i]);
+                if (c < best) { axis = a; plane = i + 1; best = c; }
+            }
+        }
+        const float noSplit = fm(half_area(nd.bmin, nd.bmax), __uint2float_rn(count));
+        int split = !(best >= noSplit);
+        uint32_t L = 0;
+        if (split) {
+            for (int b = 0; b < plane; b++) L += sCnt[axis][b];
+            if (L == 0 || L == count) split = 0;
+        }
+        sAxis = axis; sPlane = plane; sSplit = split; sL = L;
+        if (split) {
+            const uint32_t child = atomicAdd(&counters[0], 2u);
+            sChild = child;
+            enqueue_child(child, L, nextBig, nextSmall, counters);
+            enqueue_child(child + 1, count - L, nextBig, nextSmall, counters);
+        }
+    }
+    __syncthreads();
+
+    if (!sSplit) {
+        // leaf: its segment is final
+        for (uint32_t i = tid; i < count; i += kThreads) finalIdx[first + i] = src[first + i];
+        return;
+    }
+
+    // ---- 3. partition (bvh.cpp:56-63) through the closed form of the swap loop ----
+    const int axis = sAxis, plane = sPlane;
+    const uint32_t L = sL, last = first + count - 1;
+    const float lo = nd.cmin[axis];
+    const float sc = __fdiv_rn(8.0f, fs(nd.cmax[axis], lo));
+    auto is_left = [&](uint32_t t) -> bool {
+        const float4 ce = __ldg(tris + 4ull * t + 3);
+        const float c = axis == 0 ? ce.x : (axis == 1 ? ce.y : ce.z);
+        return bin_of(c, lo, sc) < plane;
+    };
+    // prefix [first, first+L): rank the holes from the left
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < L; base += kThreads) {
+        const uint32_t i = base + tid;
+        uint32_t flag = 0;
+        if (i < L) flag = is_left(src[first + i]) ? 0u : 1u;
+        uint32_t tot;
+        const uint32_t r = block_exclusive_scan(flag, warpSums, tot) + carry;
+        if (i < L) {
+            rankScratch[first + i] = r;
+            if (flag) holePos[first + r] = first + i;
+        }
+        carry += tot;
+    }
+    const uint32_t h = carry;
+    // suffix (first+L .. last], walked from the right end: rank the left elements
+    carry = 0;
+    const uint32_t nSuf = count - L;
+    for (uint32_t base = 0; base < nSuf; base += kThreads) {
+        const uint32_t s = base + tid;               // back index
+        uint32_t flag = 0;
+        if (s < nSuf) flag = is_left(src[last - s]) ? 1u : 0u;
+        uint32_t tot;
+        const uint32_t r = block_exclusive_scan(flag, warpSums, tot) + carry;
+        if (s < nSuf) {
+            rankScratch[last - s] = r;
+            if (flag) sleftPos[first + r] = last - s;
+        }
+        carry += tot;
+    }
+    __syncthreads();
+
+    // placement + children's bounds (UpdateNodeBounds of both children)
+    float b[24];
+#pragma unroll
+    for (int k = 0; k < 24; k++) b[k] = ((k / 3) & 1) ? -1e30f : 1e30f;   // [lo hi clo chi] x {left, right}
+    for (uint32_t i = tid; i < count; i += kThreads) {
+        const uint32_t p = first + i;
+        const uint32_t t = src[p];
+        const float4 v0 = __ldg(tris + 4ull * t), v1 = __ldg(tris + 4ull * t + 1), v2 = __ldg(tris + 4ull * t + 2), ce = __ldg(tris + 4ull * t + 3);
+        const float c = axis == 0 ? ce.x : (axis == 1 ? ce.y : ce.z);
+        const bool left = bin_of(c, lo, sc) < plane;
+        const uint32_t r = rankScratch[p];
+        uint32_t d;
+        if (i < L) {
+            if (left) d = p;
+            else d = (r == 0) ? last : sleftPos[first + r - 1] - 1;
+        } else {
+            if (left) d = holePos[first + r];
+            else if (i == L) d = (h == 0) ? last : sleftPos[first + h - 1] - 1;
+            else d = p - 1;
+        }
+        dst[d] = t;
+        float* q = left ? b : b + 12;
+        q[0] = fminf(q[0], fminf(fminf(v0.x, v1.x), v2.x)); q[3] = fmaxf(q[3], fmaxf(fmaxf(v0.x, v1.x), v2.x));
+        q[1] = fminf(q[1], fminf(fminf(v0.y, v1.y), v2.y)); q[4] = fmaxf(q[4], fmaxf(fmaxf(v0.y, v1.y), v2.y));
+        q[2] = fminf(q[2], fminf(fminf(v0.z, v1.z), v2.z)); q[5] = fmaxf(q[5], fmaxf(fmaxf(v0.z, v1.z), v2.z));
+        q[6] = fminf(q[6], ce.x); q[9] = fmaxf(q[9], ce.x);
+        q[7] = fminf(q[7], ce.y); q[10] = fmaxf(q[10], ce.y);
+        q[8] = fminf(q[8], ce.z); q[11] = fmaxf(q[11], ce.z);
+    }
+#pragma unroll
+    for (int k = 0; k < 24; k++) {
+        const bool isMax = ((k % 12) / 3) & 1;
+        const float v = isMax ? warp_max(b[k]) : warp_min(b[k]);
+        if ((tid & 31) == 0) red[tid >> 5][k] = v;
+    }
+    __syncthreads();
+    if (tid < 24) {
+        const bool isMax = ((tid % 12) / 3) & 1;
+        float v = red[0][tid];
+        for (int w = 1; w < kThreads / 32; w++) v = isMax ? fmaxf(v, red[w][tid]) : fminf(v, red[w][tid]);
+        red[0][tid] = v;
+    }
+    __syncthreads();
+    if (tid < 2) {
+        const float* q = red[0] + 12 * tid;
+        BNode c;
+        for (int k = 0; k < 3; k++) { c.bmin[k] = q[k]; c.bmax[k] = q[3 + k]; c.cmin[k] = q[6 + k]; c.cmax[k] = q[9 + k]; }
+        c.first = tid == 0 ? first : first + L;
+        c.count = tid == 0 ? L : count - L;
+        c.left = 0;
+        c.depth = nd.depth + 1;
+        nodes[sChild + tid] = c;
+    }
+    if (tid == 0) nodes[nodeId].left = sChild;
+}
+
+// One level for small nodes (count <= kSmall): one thread per node runs the host algorithm as is --
+// bins, sweep, the swap loop itself, children's bounds -- so nothing needs to be re-derived.
+__global__ void __launch_bounds__(128) k_level_small(const uint32_t* __restrict__ list, int nList, BNode* __restrict__ nodes,
+                                                     const float4* __restrict__ tris, const uint32_t* __restrict__ src,
+                                                     uint32_t* __restrict__ dst, uint32_t* __restrict__ finalIdx,
+                                                     uint32_t* __restrict__ nextBig, uint32_t* __restrict__ nextSmall,
+                                                     uint32_t* __restrict__ counters)
+{
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nList) return;
+    const uint32_t nodeId = list[li];
+    const BNode nd = nodes[nodeId];
+    const uint32_t first = nd.first, count = nd.count;
+    uint32_t idx[kSmall];
+    for (uint32_t i = 0; i < count; i++) idx[i] = src[first + i];
+
+    float best = 1e30f;
+    int axis = 0, plane = 0;
+    for (int a = 0; a < 3; a++) {
+        const float lo = nd.cmin[a], hi = nd.cmax[a];
+        if (lo == hi) continue;
+        const float scale = __fdiv_rn(8.0f, fs(hi, lo));
+        float binLo[kBins][3], binHi[kBins][3];
+        int cnt[kBins];
+        for (int b = 0; b < kBins; b++) {
+            cnt[b] = 0;
+            for (int k = 0; k < 3; k++) { binLo[b][k] = 1e30f; binHi[b][k] = -1e30f; }
+        }
+        for (uint32_t i = 0; i < count; i++) {
+            const uint32_t t = idx[i];
+            const float4 v0 = __ldg(tris + 4ull * t), v1 = __ldg(tris + 4ull * t + 1), v2 = __ldg(tris + 4ull * t + 2), ce = __ldg(tris + 4ull * t + 3);
+            const float c = a == 0 ? ce.x : (a == 1 ? ce.y : ce.z);
+            const int b = bin_of(c, lo, scale);
+            cnt[b]++;
+            binLo[b][0] = fminf(binLo[b][0], fminf(fminf(v0.x, v1.x), v2.x)); binHi[b][0] = fmaxf(binHi[b][0], fmaxf(fmaxf(v0.x, v1.x), v2.x));
+            binLo[b][1] = fminf(binLo[b][1], fminf(fminf(v0.y, v1.y), v2.y)); binHi[b][1] = fmaxf(binHi[b][1], fmaxf(fmaxf(v0.y, v1.y), v2.y));
+            binLo[b][2] = fminf(binLo[b][2], fminf(fminf(v0.z, v1.z), v2.z)); binHi[b][2] = fmaxf(binHi[b][2], fmaxf(fmaxf(v0.z, v1.z), v2.z));
+        }
+        float costL[kBins - 1], costR[kBins - 1];
+        float lLo[3] = {1e30f, 1e30f, 1e30f}, lHi[3] = {-1e30f, -1e30f, -1e30f};
+        float rLo[3] = {1e30f, 1e30f, 1e30f}, rHi[3] = {-1e30f, -1e30f, -1e30f};
+        int nL = 0, nR = 0;
+        for (int i = 0; i < kBins - 1; i++) {
+            nL += cnt[i];
+            for (int k = 0; k < 3; k++) {
+                lLo[k] = binLo[i][k] < lLo[k] ? binLo[i][k] : lLo[k];
+                lHi[k] = binHi[i][k] > lHi[k] ? binHi[i][k] : lHi[k];
+            }
+            costL[i] = fm(__int2float_rn(nL), half_area(lLo, lHi));
+            const int rb = kBins - 2 - i;
+            nR += cnt[rb + 1];
+            for (int k = 0; k < 3; k++) {
+                rLo[k] = binLo[rb][k] < rLo[k] ? binLo[rb][k] : rLo[k];
+                rHi[k] = binHi[rb][k] > rHi[k] ? binHi[rb][k] : rHi[k];
+            }
+            costR[rb] = fm(__int2float_rn(nR), half_area(rLo, rHi));
+        }
+        for (int i = 0; i < kBins - 1; i++) {
+            const float c = fa(costL[i], costR[i]);
+            if (c < best) { axis = a; plane = i + 1; best = c; }
+        }
+    }
+    const float noSplit = fm(half_area(nd.bmin, nd.bmax), __uint2float_rn(count));
+    bool split = !(best >= noSplit);
+    int i = 0, j = (int)count - 1;
+    if (split) {
+        const float lo = nd.cmin[axis];
+        const float sc = __fdiv_rn(8.0f, fs(nd.cmax[axis], lo));
+        while (i <= j) {
+            const float4 ce = __ldg(tris + 4ull * idx[i] + 3);
+            const float c = axis == 0 ? ce.x : (axis == 1 ? ce.y : ce.z);
+            if (bin_of(c, lo, sc) < plane) i++;
+            else { const uint32_t t = idx[i]; idx[i] = idx[j]; idx[j] = t; j--; }
+        }
+        if (i == 0 || i == (int)count) split = false;   // (the swap loop only permuted a copy)
+    }
+    if (!split) {
+        for (uint32_t k = 0; k < count; k++) finalIdx[first + k] = src[first + k];
+        return;
+    }
+    const uint32_t L = (uint32_t)i;
+    for (uint32_t k = 0; k < count; k++) dst[first + k] = idx[k];
+    const uint32_t child = atomicAdd(&counters[0], 2u);
+    for (int side = 0; side < 2; side++) {
+        BNode c;
+        for (int k = 0; k < 3; k++) { c.bmin[k] = 1e30f; c.bmax[k] = -1e30f; c.cmin[k] = 1e30f; c.cmax[k] = -1e30f; }
+        const uint32_t b0 = side ? L : 0, b1 = side ? count : L;
+        for (uint32_t k = b0; k < b1; k++) {
+            const uint32_t t = idx[k];
+            const float4 v0 = __ldg(tris + 4ull * t), v1 = __ldg(tris + 4ull * t + 1), v2 = __ldg(tris + 4ull * t + 2), ce = __ldg(tris + 4ull * t + 3);
+            c.bmin[0] = fminf(c.bmin[0], fminf(fminf(v0.x, v1.x), v2.x)); c.bmax[0] = fmaxf(c.bmax[0], fmaxf(fmaxf(v0.x, v1.x), v2.x));
+            c.bmin[1] = fminf(c.bmin[1], fminf(fminf(v0.y, v1.y), v2.y)); c.bmax[1] = fmaxf(c.bmax[1], fmaxf(fmaxf(v0.y, v1.y), v2.y));
+            c.bmin[2] = fminf(c.bmin[2], fminf(fminf(v0.z, v1.z), v2.z)); c.bmax[2] = fmaxf(c.bmax[2], fmaxf(fmaxf(v0.z, v1.z), v2.z));
+            c.cmin[0] = fminf(c.cmin[0], ce.x); c.cmax[0] = fmaxf(c.cmax[0], ce.x);
+            c.cmin[1] = fminf(c.cmin[1], ce.y); c.cmax[1] = fmaxf(c.cmax[1], ce.y);
+            c.cmin[2] = fminf(c.cmin[2], ce.z); c.cmax[2] = fmaxf(c.cmax[2], ce.z);
+        }
+        c.first = first + b0;
+        c.count = b1 - b0;
+        c.left = 0;
+        c.depth = nd.depth + 1;
+        nodes[child + side] = c;
+        enqueue_child(child + side, c.count, nextBig, nextSmall, counters);
+    }
+    nodes[nodeId].left = child;
+}
+
+// ---- renumbering into the reference's node order ---------------------------------------------------
+// bottom-up: slots allocated inside a recursively numbered subtree
+__global__ void __launch_bounds__(256) k_sizes(const uint32_t* __restrict__ list, int n, const BNode* __restrict__ nodes, BAux* __restrict__ aux)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t id = list[i];
+    const uint32_t l = nodes[id].left;
+    aux[id].sFull = l ? 2u + aux[l].sFull + aux[l + 1].sFull : 0u;
+}
+
+// The first four levels (nodes of depth <= 3 are numbered serially, their grandchildren at depth 4
+// are the roots of the independent jobs), by one thread -- at most 15 + 16 nodes.
+__global__ void k_number_top(const BNode* __restrict__ nodes, BAux* __restrict__ aux, uint32_t* __restrict__ usedMax)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // depth-first walk mirroring bvh.cpp:46-96 with `depth == 3` deferral
+    uint32_t stackId[40];
+    int sp = 0;
+    uint32_t nextFree = 2;
+    uint32_t jobs[16];
+    int nJobs = 0;
+    aux[0].ref = 0;
+    // explicit recursion: visit(node): if split { allocate pair; left: recurse or defer; right: recurse or defer }
+    // pre-order with the right child pushed first reproduces "left subtree fully numbered before the right one"
+    stackId[sp++] = 0;
+    while (sp) {
+        const uint32_t id = stackId[--sp];
+        const BNode nd = nodes[id];
+        if (!nd.left) continue;
+        aux[nd.left].ref = nextFree;
+        aux[nd.left + 1].ref = nextFree + 1;
+        nextFree += 2;
+        if (nd.depth == 3) {
+            jobs[nJobs++] = nd.left;
+            jobs[nJobs++] = nd.left + 1;
+        } else {
+            stackId[sp++] = nd.left + 1;
+            stackId[sp++] = nd.left;
+        }
+    }
+    // NOTE: the host walk allocates a node's pair BEFORE descending, and descends left first; the stack
+    // order above visits the left child's subtree completely before the right child is popped.
+    uint32_t base = nextFree, used = nextFree;
+    for (int j = 0; j < nJobs; j++) {
+        aux[jobs[j]].alloc = base;
+        const uint32_t end = base + aux[jobs[j]].sFull;
+        used = end > used ? end : used;
+        base += nodes[jobs[j]].count * 2u;
+    }
+    *usedMax = used;
+}
+
+// top-down inside the jobs (depth >= 4): children pair at alloc, left subtree numbered first
+__global__ void __launch_bounds__(256) k_number_level(const uint32_t* __restrict__ list, int n, const BNode* __restrict__ nodes, BAux* __restrict__ aux)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t id = list[i];
+    const BNode nd = nodes[id];
+    if (nd.depth < 4 || !nd.left) return;
+    const uint32_t a = aux[id].alloc;
+    aux[nd.left].ref = a;
+    aux[nd.left + 1].ref = a + 1;
+    aux[nd.left].alloc = a + 2;
+    aux[nd.left + 1].alloc = a + 2 + aux[nd.left].sFull;
+}
+
+// final node array in the reference layout (bvh.h:11-21)
+__global__ void __launch_bounds__(256) k_emit(const BNode* __restrict__ nodes, const BAux* __restrict__ aux, int nTemp, float4* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nTemp) return;
+    const BNode nd = nodes[i];
+    const uint32_t r = aux[i].ref;
+    const uint32_t leftFirst = nd.left ? aux[nd.left].ref : nd.first;
+    const uint32_t triCount = nd.left ? 0u : nd.count;
+    out[2ull * r] = make_float4(nd.bmin[0], nd.bmin[1], nd.bmin[2], __uint_as_float(leftFirst));
+    out[2ull * r + 1] = make_float4(nd.bmax[0], nd.bmax[1], nd.bmax[2], __uint_as_float(triCount));
+}
+
+} // namespace uvrt_bvh

@@ -4,6 +4,7 @@
 // path RayTracer drives (raytracer.cpp:12-143).  No torch, no C++ types in the interface.
 #include "../../include/uvrt.h"
 #include "uvrt_kernels.cuh"
+#include "uvrt_bvh_build.cuh"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -12,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -128,6 +130,7 @@ struct uvrt_ctx {
     uint32_t* dSeeds = nullptr;
     float* dSeedPos = nullptr;
     int seedCap = 0;
+    bool poolTuned = false;
     void* dFlush = nullptr;              // L2 flush scratch
     // ray binning (counting sort by direction / origin cell); the tables live in the ray slots
     int binRays = 1, binY = 16, binT = 32, binP = 128;   // 65,536 bins: best of the sweeps
@@ -682,6 +685,138 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
     ctx->sceneTame = tame ? 1 : 0;
     ctx->rootRef = child_ref(0);
     ctx->uploadBytes = (int64_t)total;
+    return UVRT_OK;
+}
+
+// ---- device BVH build (uvrt_bvh_build.cuh) ----------------------------------------------------------
+int uvrt_build_bvh(uvrt_ctx* ctx, const void* trisHost, int nTris, void* nodesOut, int nodeCapacity,
+                   uint32_t* triIdxOut, uint32_t* nodesUsedOut, void* trisOut)
+{
+    using namespace uvrt_bvh;
+    if (!ctx) return UVRT_ERR_INVALID;
+    if (!trisHost || nTris <= 0 || !nodesOut || !triIdxOut)
+        return fail(ctx, UVRT_ERR_INVALID, "build_bvh: null pointer or empty mesh");
+    Bind b(ctx);
+    const bool verbose = getenv("UVRT_BVH_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tPhase = now();
+    auto phase = [&](const char* name) {
+        if (!verbose) return;
+        cudaStreamSynchronize(ctx->stream);
+        double t = now();
+        fprintf(stderr, "[uvrt_build_bvh] %-10s %8.3f ms\n", name, t - tPhase);
+        tPhase = t;
+    };
+    const size_t n = (size_t)nTris, maxNodes = 2 * n + 2;
+    float4* dTris = nullptr; uint32_t *dIdxA = nullptr, *dIdxB = nullptr, *dFinal = nullptr, *dRank = nullptr, *dHole = nullptr, *dSleft = nullptr;
+    uint32_t *dList = nullptr, *dListSmall = nullptr, *dCounters = nullptr, *dAcc = nullptr, *dUsed = nullptr;
+    BNode* dNodes = nullptr; BAux* dAux = nullptr; float4* dOut = nullptr;
+    std::vector<void*> owned;
+    // stream-ordered allocations from the device's pool: cudaMalloc/cudaFree cost tens of milliseconds
+    // per build here, the pool hands the same memory back on the next build
+    if (!ctx->poolTuned) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        ctx->poolTuned = true;
+    }
+    auto cleanup = [&]() { for (void* p : owned) cudaFreeAsync(p, ctx->stream); };
+#define BALLOC(ptr, bytes)                                                                            \
+    do {                                                                                              \
+        cudaError_t e_ = cudaMallocAsync((void**)&(ptr), (bytes), ctx->stream);                                         \
+        if (e_ != cudaSuccess) { cleanup(); return fail(ctx, UVRT_ERR_NO_MEMORY, "build_bvh: %s", cudaGetErrorString(e_)); } \
+        owned.push_back((void*)(ptr));                                                                \
+    } while (0)
+#define BCK(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) { cleanup(); return fail(ctx, UVRT_ERR_CUDA, "build_bvh: %s failed: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
+    BALLOC(dTris, n * 64);
+    BALLOC(dIdxA, n * 4); BALLOC(dIdxB, n * 4); BALLOC(dFinal, n * 4);
+    BALLOC(dRank, n * 4); BALLOC(dHole, n * 4); BALLOC(dSleft, n * 4);
+    BALLOC(dList, maxNodes * 4); BALLOC(dListSmall, maxNodes * 4); BALLOC(dCounters, 16); BALLOC(dAcc, 64); BALLOC(dUsed, 4);
+    BALLOC(dNodes, maxNodes * sizeof(BNode)); BALLOC(dAux, maxNodes * sizeof(BAux));
+    const size_t outSlots = 2 * n + 64;
+    BALLOC(dOut, outSlots * 32);
+    cudaStream_t st = ctx->stream;
+    phase("alloc");
+    BCK(cudaMemcpyAsync(dTris, trisHost, n * 64, cudaMemcpyHostToDevice, st));
+    BCK(cudaMemsetAsync(dAux, 0, maxNodes * sizeof(BAux), st));
+    BCK(cudaMemsetAsync(dOut, 0, outSlots * 32, st));
+    const uint32_t accInit[12] = {~0u, ~0u, ~0u, 0, 0, 0, ~0u, ~0u, ~0u, 0, 0, 0};
+    BCK(cudaMemcpyAsync(dAcc, accInit, sizeof accInit, cudaMemcpyHostToDevice, st));
+    k_centroids<<<grid_for(nTris, 256), 256, 0, st>>>(dTris, dIdxA, nTris);
+    k_root_bounds<<<std::min<unsigned>(grid_for(nTris, 256), 1184u), 256, 0, st>>>(dTris, nTris, dAcc);
+    k_init_root<<<1, 1, 0, st>>>(dNodes, dAcc, nTris, dList, dCounters);
+    ctx->launches += 3;
+    phase("upload+root");
+    // level by level; big nodes (block per node) and small nodes (thread per node) have their own lists
+    struct Level { uint32_t bigOff, nBig, smallOff, nSmall; };
+    std::vector<Level> levels;
+    uint32_t bigOff = 0, smallOff = 0, nBig = 1, nSmall = 0;
+    uint32_t *src = dIdxA, *dst = dIdxB;
+    while (nBig + nSmall > 0) {
+        if (levels.size() > 200) { cleanup(); return fail(ctx, UVRT_ERR_INVALID, "build_bvh: tree deeper than 200 levels"); }
+        levels.push_back({bigOff, nBig, smallOff, nSmall});
+        BCK(cudaMemsetAsync(dCounters + 1, 0, 8, st));
+        uint32_t* nextBig = dList + bigOff + nBig;
+        uint32_t* nextSmall = dListSmall + smallOff + nSmall;
+        if (nBig)
+            k_level<<<nBig, kThreads, 0, st>>>(dList + bigOff, dNodes, dTris, src, dst, dFinal, dRank, dHole, dSleft,
+                                               nextBig, nextSmall, dCounters);
+        if (nSmall)
+            k_level_small<<<grid_for(nSmall, 128), 128, 0, st>>>(dListSmall + smallOff, (int)nSmall, dNodes, dTris, src, dst, dFinal,
+                                                                 nextBig, nextSmall, dCounters);
+        ctx->launches += (nBig ? 1 : 0) + (nSmall ? 1 : 0);
+        uint32_t next[2] = {0, 0};
+        BCK(cudaMemcpyAsync(next, dCounters + 1, 8, cudaMemcpyDeviceToHost, st));
+        BCK(cudaStreamSynchronize(st));
+        if (verbose) fprintf(stderr, "[uvrt_build_bvh] level %2zu: %8u big %8u small ", levels.size() - 1, nBig, nSmall);
+        phase("");
+        bigOff += nBig;
+        smallOff += nSmall;
+        nBig = next[0];
+        nSmall = next[1];
+        std::swap(src, dst);
+    }
+    uint32_t nTemp = 0;
+    BCK(cudaMemcpyAsync(&nTemp, dCounters, 4, cudaMemcpyDeviceToHost, st));
+    BCK(cudaStreamSynchronize(st));
+    // renumber: subtree sizes bottom-up, reference indices top-down
+    for (int d = (int)levels.size() - 1; d >= 0; d--) {
+        const Level& lv = levels[d];
+        if (lv.nBig) k_sizes<<<grid_for(lv.nBig, 256), 256, 0, st>>>(dList + lv.bigOff, (int)lv.nBig, dNodes, dAux);
+        if (lv.nSmall) k_sizes<<<grid_for(lv.nSmall, 256), 256, 0, st>>>(dListSmall + lv.smallOff, (int)lv.nSmall, dNodes, dAux);
+    }
+    k_number_top<<<1, 1, 0, st>>>(dNodes, dAux, dUsed);
+    for (size_t d = 4; d < levels.size(); d++) {
+        const Level& lv = levels[d];
+        if (lv.nBig) k_number_level<<<grid_for(lv.nBig, 256), 256, 0, st>>>(dList + lv.bigOff, (int)lv.nBig, dNodes, dAux);
+        if (lv.nSmall) k_number_level<<<grid_for(lv.nSmall, 256), 256, 0, st>>>(dListSmall + lv.smallOff, (int)lv.nSmall, dNodes, dAux);
+    }
+    k_emit<<<grid_for(nTemp, 256), 256, 0, st>>>(dNodes, dAux, (int)nTemp, dOut);
+    ctx->launches += (int64_t)levels.size() * 4 + 2;
+    uint32_t used = 0;
+    BCK(cudaMemcpyAsync(&used, dUsed, 4, cudaMemcpyDeviceToHost, st));
+    BCK(cudaStreamSynchronize(st));
+    phase("renumber");
+    if ((long long)used > (long long)nodeCapacity) {
+        cleanup();
+        return fail(ctx, UVRT_ERR_INVALID, "build_bvh: %u node slots needed, nodeCapacity is %d", used, nodeCapacity);
+    }
+    BCK(cudaMemcpyAsync(nodesOut, dOut, (size_t)used * 32, cudaMemcpyDeviceToHost, st));
+    BCK(cudaMemcpyAsync(triIdxOut, dFinal, n * 4, cudaMemcpyDeviceToHost, st));
+    if (trisOut) BCK(cudaMemcpyAsync(trisOut, dTris, n * 64, cudaMemcpyDeviceToHost, st));
+    BCK(cudaStreamSynchronize(st));
+    if (nodesUsedOut) *nodesUsedOut = used;
+    phase("download");
+    cleanup();
+    phase("free");
+#undef BALLOC
+#undef BCK
     return UVRT_OK;
 }
 

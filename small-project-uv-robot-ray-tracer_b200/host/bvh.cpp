@@ -19,6 +19,7 @@
 // array is allocated with the slack the numbering scheme really needs (2N + 64) and nodesUsed
 // reports the true extent (the reference under-allocates: SURVEY App. B-3).
 #include "precomp.h"
+#include "../../include/uvrt.h"
 #include <algorithm>
 
 using namespace Tmpl8;
@@ -50,6 +51,22 @@ BVH::BVH(Mesh* m) : mesh(m)
     bvhNode = (BVHNode*)p;
     triIdx = new uint[m->triangleCount > 0 ? m->triangleCount : 1];
     if (bvhNode) Build();
+}
+
+BVH::BVH(Mesh* m, uvrt_ctx* ctx) : mesh(m)
+{
+    nodeCapacity = (uint)m->triangleCount * 2u + 64u;
+    void* p = nullptr;
+    if (posix_memalign(&p, 64, sizeof(BVHNode) * (size_t)nodeCapacity) != 0) p = nullptr;
+    bvhNode = (BVHNode*)p;
+    triIdx = new uint[m->triangleCount > 0 ? m->triangleCount : 1];
+    ok = false;
+    if (!bvhNode || m->triangleCount <= 0) return;
+    memset(bvhNode, 0, sizeof(BVHNode) * (size_t)nodeCapacity);
+    uint32_t used = 0;
+    // centroids are written back into the mesh, as Build() does (bvh.cpp:23 of the reference)
+    ok = uvrt_build_bvh(ctx, m->triangles, m->triangleCount, bvhNode, (int)nodeCapacity, triIdx, &used, m->triangles) == UVRT_OK;
+    nodesUsed = ok ? used : 0;
 }
 
 BVH::~BVH()

@@ -3,6 +3,7 @@
 #pragma once
 
 namespace Tmpl8 { class Mesh; }
+struct uvrt_ctx;
 
 // 32-byte node, identical in memory to the reference's (bvh.h:11-21) and to cl/tools.cl:39-45
 struct BVHNode {
@@ -23,6 +24,9 @@ class BVH {
 public:
     BVH() = default;
     explicit BVH(Tmpl8::Mesh* mesh);
+    // Builds on the device through uvrt_build_bvh (same tree, numbering and triIdx order as Build()).
+    // `ok` is false when the backend call failed; the arrays are then empty.
+    BVH(Tmpl8::Mesh* mesh, uvrt_ctx* ctx);
     ~BVH();
     BVH(const BVH&) = delete;
     BVH& operator=(const BVH&) = delete;
@@ -34,6 +38,7 @@ public:
     uint nodesUsed = 0;
     BVHNode* bvhNode = 0;
     uint nodeCapacity = 0;   // allocated slots (2N + 64)
+    bool ok = true;
 
 private:
     struct Bounds3 { float lo[3], hi[3]; };

@@ -153,8 +153,10 @@ void Mesh::LoadMesh()
     DetermineFloorHeight();
 
     std::cout << "Vertex count: " << vertexCount << " triangle count: " << triangleCount << std::endl;
-    bvh = new BVH(this);
-    std::cout << "BVH size: " << bvh->nodesUsed << std::endl;
+    if (buildBvhOnLoad) {
+        bvh = new BVH(this);
+        std::cout << "BVH size: " << bvh->nodesUsed << std::endl;
+    }
     BindMesh();
     loadedMesh = true;
 }
@@ -180,7 +182,7 @@ void Mesh::SetTriangles(const Tri* tris, int n, bool buildBvh)
         }
     }
     DetermineFloorHeight();
-    if (buildBvh) bvh = new BVH(this);
+    if (buildBvh && buildBvhOnLoad) bvh = new BVH(this);
     loadedMesh = true;
 }
 

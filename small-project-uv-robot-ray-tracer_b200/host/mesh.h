@@ -30,6 +30,9 @@ public:
     void SetTriangles(const Tri* tris, int n, bool buildBvh = true);
 
     char modelFile[32] = "C046_1";
+    // false: LoadMesh / SetTriangles leave `bvh` empty and RayTracer::Init builds it on the device
+    // (uvrt_build_bvh) -- the reference always builds on the CPU inside LoadMesh (mesh.cpp:96).
+    bool buildBvhOnLoad = true;
 
     Tri* triangles = 0;
     int triangleCount = 0;

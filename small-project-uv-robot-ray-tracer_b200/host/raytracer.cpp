@@ -53,10 +53,22 @@ void RayTracer::Init(Mesh* m)
     launchCounter = 0;
     seedQueue.clear();
     seedQueueHead = 0;
-    if (!mesh || !mesh->loadedMesh || !mesh->bvh) {
+    if (!mesh || !mesh->loadedMesh) {
         ok = false;
         lastError = "Init: mesh not loaded";
         return;
+    }
+    if (!mesh->bvh) {
+        // Mesh::buildBvhOnLoad == false: build the tree on the device now
+        Timer t;
+        mesh->bvh = new BVH(mesh, ctx);
+        if (!mesh->bvh->ok) {
+            Check(UVRT_ERR_CUDA, "build_bvh");
+            delete mesh->bvh;
+            mesh->bvh = 0;
+            return;
+        }
+        std::cout << "BVH size: " << mesh->bvh->nodesUsed << " (device build, " << t.elapsed() * 1000.0f << " ms)" << std::endl;
     }
     UploadScene();
 }

@@ -56,6 +56,13 @@ int uvrt_sim_load_mesh(uvrt_sim* s, const char* modelFile)
     return UVRT_OK;
 }
 
+int uvrt_sim_set_device_bvh(uvrt_sim* s, int deviceBvh)
+{
+    if (!s) return UVRT_ERR_INVALID;
+    s->mesh.buildBvhOnLoad = deviceBvh == 0;
+    return UVRT_OK;
+}
+
 int uvrt_sim_set_triangles(uvrt_sim* s, const void* tris, int n)
 {
     if (!s || !tris || n <= 0) return UVRT_ERR_INVALID;

@@ -374,3 +374,56 @@ def test_error_codes_instead_of_aborts(uv, room):
     with pytest.raises(uv.UvrtError):
         uv.Context(99)
     c.close()
+
+
+def _same_tree(a, b):
+    (ta, na, ia), (tb, nb, ib) = a, b
+    assert np.array_equal(ia, ib), "triIdx differs"
+    assert ta.tobytes() == tb.tobytes(), "centroids differ"
+    pa, pb = T.reachable_preorder(na), T.reachable_preorder(nb)
+    assert np.array_equal(pa, pb), "node numbering differs"
+    assert na[pa].tobytes() == nb[pb].tobytes(), "node contents differ"
+    assert len(na) == len(nb), "nodesUsed differs"
+
+
+def test_device_bvh_build_equals_host_builder(uv, ctx, room):
+    """uvrt_build_bvh (device) against host/bvh.cpp (which equals the reference's bvh.cpp, test_host.py):
+    same triIdx order, same node numbering, same boxes -- on the room, on small and degenerate meshes
+    and on a 200k-triangle soup (deeper than the room, several partition patterns)."""
+    from importlib import import_module
+    B = import_module("small-project-uv-robot-ray-tracer_b200.binding")
+    sys_tools = __import__("sys")
+    sys_tools.path.insert(0, T.ROOT + "/tools")
+    from soup import make_soup
+    tris = room[0].copy()
+    tris[:, 12:16] = 0
+    _same_tree(ctx.build_bvh(tris), B.build_bvh(tris))
+    rng = np.random.default_rng(21)
+    for n in (1, 2, 3, 5, 17, 64, 200, 257, 5000):
+        m = np.zeros((n, 16), dtype=np.float32)
+        c = rng.uniform(-5, 5, (n, 3))
+        for k in range(3):
+            m[:, 4 * k: 4 * k + 3] = (c + rng.uniform(-0.2, 0.2, (n, 3))).astype(np.float32)
+        if n >= 17:
+            m[5] = m[6]
+            m[7, 0:12] = m[7, 0]
+            m[9:13] = m[8]             # five identical triangles: a node that cannot be split
+        _same_tree(ctx.build_bvh(m), B.build_bvh(m))
+    soup = make_soup(200_000)
+    _same_tree(ctx.build_bvh(soup), B.build_bvh(soup))
+
+
+def test_raytracer_with_device_built_bvh(uv, room, golden):
+    """Mesh::buildBvhOnLoad = false: RayTracer::Init builds the tree with uvrt_build_bvh; the run is
+    indistinguishable from one on the host-built tree."""
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.set_device_bvh(True)
+    sim.load_mesh("testroomopt")
+    assert sim.mesh_info()["nodesUsed"] == 0
+    sim.init("lange_route")
+    tris, nodes, tri_idx = sim.mesh_data()
+    assert nodes.tobytes() == room[1].tobytes() and np.array_equal(tri_idx, room[2]) and tris.tobytes() == room[0].tobytes()
+    sim.set_params(maxIterations=1)
+    dose = sim.run()
+    assert f"{T.fnv(dose):016x}" == golden["pass_lange_route"]["fnv_dose"]
+    sim.close()

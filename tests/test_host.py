@@ -188,3 +188,51 @@ def test_shared_reciprocal_division_is_proven_exact(tmp_path):
     r = subprocess.run([exe, "26"], capture_output=True, text=True, timeout=600)
     assert "FAILURES 0" in r.stdout and r.returncode == 0, r.stdout[-500:]
     assert "hard cases (|num| <= 8) 46517418" in r.stdout
+
+
+def test_swap_partition_closed_form():
+    """The device BVH builder (csrc/uvrt_bvh_build.cuh) places every element of the reference's in-place
+    partition loop (bvh.cpp:56-63) independently through a closed form of the loop's result.  Check the
+    closed form against the loop itself on random inputs."""
+    import random
+
+    def loop(a, left):
+        a = list(a)
+        i, j = 0, len(a) - 1
+        while i <= j:
+            if left[a[i]]:
+                i += 1
+            else:
+                a[i], a[j] = a[j], a[i]
+                j -= 1
+        return a, i
+
+    def closed_form(a, left):
+        n = len(a)
+        L = sum(1 for x in a if left[x])
+        last = n - 1
+        dst = [None] * n
+        holes = [p for p in range(L) if not left[a[p]]]                       # prefix, from the left
+        slefts = [q for q in range(last, L - 1, -1) if left[a[q]]]            # suffix, from the right
+        h = len(holes)
+        for p in range(L):
+            if left[a[p]]:
+                dst[p] = a[p]
+        for k in range(h):
+            dst[holes[k]] = a[slefts[k]]
+            dst[last if k == 0 else slefts[k - 1] - 1] = a[holes[k]]
+        for q in range(L, n):
+            if left[a[q]]:
+                continue
+            if q == L:
+                dst[last if h == 0 else slefts[h - 1] - 1] = a[q]
+            else:
+                dst[q - 1] = a[q]
+        return dst, L
+
+    rnd = random.Random(5)
+    for _ in range(50000):
+        n = rnd.randint(1, 40)
+        p = rnd.random()
+        left = [rnd.random() < p for _ in range(n)]
+        assert loop(range(n), left) == closed_form(range(n), left)

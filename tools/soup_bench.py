@@ -40,6 +40,12 @@ def main():
     info = ctx.scene_info()
     print(json.dumps({"tris": args.tris, "make_s": round(t1 - t0, 2), "bvh_build_s": round(t2 - t1, 2), "scene": info,
                       "floor": float(sim.mesh_info()["floor"]), "tame": ctx.get_option("scene_tame")}), flush=True)
+    tb = time.perf_counter()
+    dt, dn, di = ctx.build_bvh(tris)
+    tb = time.perf_counter() - tb
+    ht, hn, hi = sim.mesh_data()
+    print(json.dumps({"device_bvh_build_s": round(tb, 3), "same_triIdx": bool(np.array_equal(di, hi)),
+                      "same_nodes": bool(dn.tobytes() == hn.tobytes())}), flush=True)
     floor = sim.mesh_info()["floor"]
     pos = sim.positions
     for P in [int(x) for x in args.rays.split(",")]:
