@@ -219,14 +219,16 @@ class Context:
         self.check(self.L.uvrt_upload_scene(self.h, _p(tris), tris.shape[0], _p(nodes), n_nodes, _p(tri_idx)))
         self.n_tris = tris.shape[0]
 
-    def build_bvh(self, tris):
-        """Device BVH build. Returns (tris with centroids, nodes, triIdx) like binding.build_bvh()."""
+    def build_bvh(self, tris, out=None):
+        """Device BVH build. Returns (tris with centroids, nodes, triIdx) like binding.build_bvh().
+        out: optional preallocated (tris (n,16) f32, nodes (2n+64) NODE_DTYPE, triIdx (n) u32) to write into."""
         t = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 16)
         n = t.shape[0]
         cap = 2 * n + 64
-        nodes = np.zeros(cap, dtype=NODE_DTYPE)
-        tri_idx = np.zeros(n, dtype=np.uint32)
-        out_tris = np.zeros_like(t)
+        if out is None:
+            out = (np.zeros_like(t), np.zeros(cap, dtype=NODE_DTYPE), np.zeros(n, dtype=np.uint32))
+        out_tris, nodes, tri_idx = out
+        assert out_tris.shape == t.shape and len(nodes) >= cap and len(tri_idx) == n
         used = C.c_uint32()
         self.check(self.L.uvrt_build_bvh(self.h, _p(t), n, _p(nodes), cap, _p(tri_idx), C.byref(used), _p(out_tris)))
         return out_tris, nodes[: used.value], tri_idx

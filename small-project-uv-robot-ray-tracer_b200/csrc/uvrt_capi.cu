@@ -709,7 +709,10 @@ int uvrt_build_bvh(uvrt_ctx* ctx, const void* trisHost, int nTris, void* nodesOu
     };
     const size_t n = (size_t)nTris, maxNodes = 2 * n + 2;
     float4* dTris = nullptr; uint32_t *dIdxA = nullptr, *dIdxB = nullptr, *dFinal = nullptr, *dRank = nullptr, *dHole = nullptr, *dSleft = nullptr;
-    uint32_t *dList = nullptr, *dListSmall = nullptr, *dCounters = nullptr, *dAcc = nullptr, *dUsed = nullptr;
+    uint32_t *dCounters = nullptr, *dAcc = nullptr, *dUsed = nullptr, *dChunkMap = nullptr, *dTotalChunks = nullptr;
+    uint32_t* dList[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    HugeInfo* dHugeInfo[2] = {nullptr, nullptr};
+    HugeState* dHugeState = nullptr; uint2 *dChunkCnt = nullptr, *dChunkOff = nullptr;
     BNode* dNodes = nullptr; BAux* dAux = nullptr; float4* dOut = nullptr;
     std::vector<void*> owned;
     // stream-ordered allocations from the device's pool: cudaMalloc/cudaFree cost tens of milliseconds
@@ -734,10 +737,20 @@ int uvrt_build_bvh(uvrt_ctx* ctx, const void* trisHost, int nTris, void* nodesOu
         cudaError_t e_ = (call);                                                                      \
         if (e_ != cudaSuccess) { cleanup(); return fail(ctx, UVRT_ERR_CUDA, "build_bvh: %s failed: %s", #call, cudaGetErrorString(e_)); } \
     } while (0)
+    // the nodes of one level own disjoint index segments, so a level has at most n / (smallest size of
+    // the class) nodes of a class
+    const size_t listCap[4] = {n + 1, n / (kSmall + 1) + 2, n / (kMid + 1) + 2, n / (kHuge + 1) + 2};
+    const size_t maxChunks = n / kChunk + listCap[3] + 1;
     BALLOC(dTris, n * 64);
     BALLOC(dIdxA, n * 4); BALLOC(dIdxB, n * 4); BALLOC(dFinal, n * 4);
     BALLOC(dRank, n * 4); BALLOC(dHole, n * 4); BALLOC(dSleft, n * 4);
-    BALLOC(dList, maxNodes * 4); BALLOC(dListSmall, maxNodes * 4); BALLOC(dCounters, 16); BALLOC(dAcc, 64); BALLOC(dUsed, 4);
+    for (int k = 0; k < 2; k++) {
+        for (int c = 0; c < 4; c++) BALLOC(dList[k][c], listCap[c] * 4);
+        BALLOC(dHugeInfo[k], listCap[3] * sizeof(HugeInfo));
+    }
+    BALLOC(dHugeState, listCap[3] * sizeof(HugeState));
+    BALLOC(dChunkMap, maxChunks * 4); BALLOC(dChunkCnt, maxChunks * 8); BALLOC(dChunkOff, maxChunks * 8);
+    BALLOC(dCounters, 32); BALLOC(dAcc, 64); BALLOC(dUsed, 4); BALLOC(dTotalChunks, 4);
     BALLOC(dNodes, maxNodes * sizeof(BNode)); BALLOC(dAux, maxNodes * sizeof(BAux));
     const size_t outSlots = 2 * n + 64;
     BALLOC(dOut, outSlots * 32);
@@ -748,57 +761,69 @@ int uvrt_build_bvh(uvrt_ctx* ctx, const void* trisHost, int nTris, void* nodesOu
     BCK(cudaMemsetAsync(dOut, 0, outSlots * 32, st));
     const uint32_t accInit[12] = {~0u, ~0u, ~0u, 0, 0, 0, ~0u, ~0u, ~0u, 0, 0, 0};
     BCK(cudaMemcpyAsync(dAcc, accInit, sizeof accInit, cudaMemcpyHostToDevice, st));
+    auto lists = [&](int k) { return Lists{dList[k][0], dList[k][1], dList[k][2], dList[k][3], dHugeInfo[k], dCounters}; };
     k_centroids<<<grid_for(nTris, 256), 256, 0, st>>>(dTris, dIdxA, nTris);
     k_root_bounds<<<std::min<unsigned>(grid_for(nTris, 256), 1184u), 256, 0, st>>>(dTris, nTris, dAcc);
-    k_init_root<<<1, 1, 0, st>>>(dNodes, dAcc, nTris, dList, dCounters);
+    k_init_root<<<1, 1, 0, st>>>(dNodes, dAcc, nTris, lists(0));
     ctx->launches += 3;
     phase("upload+root");
-    // level by level; big nodes (block per node) and small nodes (thread per node) have their own lists
-    struct Level { uint32_t bigOff, nBig, smallOff, nSmall; };
+    // level by level; the nodes of a level are dealt to four kernels by size
+    struct Level { uint32_t idBegin, idEnd; };
     std::vector<Level> levels;
-    uint32_t bigOff = 0, smallOff = 0, nBig = 1, nSmall = 0;
+    uint32_t cnt[5] = {1, 0, 0, 0, 0};          // [0] next temp id, [1..4] small / mid / big / huge nodes of this level
+    cnt[n <= kSmall ? 1 : n <= kMid ? 2 : n <= kHuge ? 3 : 4] = 1;
+    uint32_t idBegin = 0;
+    int cur = 0;
     uint32_t *src = dIdxA, *dst = dIdxB;
-    while (nBig + nSmall > 0) {
+    while (cnt[1] + cnt[2] + cnt[3] + cnt[4] > 0) {
         if (levels.size() > 200) { cleanup(); return fail(ctx, UVRT_ERR_INVALID, "build_bvh: tree deeper than 200 levels"); }
-        levels.push_back({bigOff, nBig, smallOff, nSmall});
-        BCK(cudaMemsetAsync(dCounters + 1, 0, 8, st));
-        uint32_t* nextBig = dList + bigOff + nBig;
-        uint32_t* nextSmall = dListSmall + smallOff + nSmall;
+        levels.push_back({idBegin, cnt[0]});
+        idBegin = cnt[0];
+        BCK(cudaMemsetAsync(dCounters + 1, 0, 16, st));
+        const Lists next = lists(1 - cur);
+        const uint32_t nSmall = cnt[1], nMid = cnt[2], nBig = cnt[3], nHuge = cnt[4];
+        if (nHuge) {
+            const HugeInfo* info = dHugeInfo[cur];
+            const unsigned chunks = (unsigned)std::min<size_t>(maxChunks, n / kChunk + nHuge);
+            k_huge_prepare<<<1, 256, 0, st>>>(dHugeInfo[cur], (int)nHuge, dChunkMap, dHugeState, dTotalChunks);
+            k_huge_bins<<<chunks, 256, 0, st>>>(info, dChunkMap, dTotalChunks, dNodes, dTris, src, dHugeState);
+            k_huge_decide<<<grid_for(nHuge, 32), 32, 0, st>>>(info, (int)nHuge, dNodes, dHugeState, next);
+            k_huge_count<<<chunks, 256, 0, st>>>(info, dChunkMap, dTotalChunks, dNodes, dTris, src, dHugeState, dChunkCnt);
+            k_huge_scan<<<nHuge, 256, 0, st>>>(info, dHugeState, dChunkCnt, dChunkOff);
+            k_huge_rank<<<chunks, 256, 0, st>>>(info, dChunkMap, dTotalChunks, dNodes, dTris, src, dHugeState, dChunkCnt, dChunkOff,
+                                                dRank, dHole, dSleft);
+            k_huge_place<<<chunks, 256, 0, st>>>(info, dChunkMap, dTotalChunks, dNodes, dTris, src, dst, dFinal, dHugeState,
+                                                 dRank, dHole, dSleft);
+            k_huge_finish<<<grid_for(nHuge, 32), 32, 0, st>>>(info, (int)nHuge, dNodes, dHugeState);
+            ctx->launches += 8;
+        }
         if (nBig)
-            k_level<<<nBig, kThreads, 0, st>>>(dList + bigOff, dNodes, dTris, src, dst, dFinal, dRank, dHole, dSleft,
-                                               nextBig, nextSmall, dCounters);
+            k_level<256><<<nBig, 256, 0, st>>>(dList[cur][2], dNodes, dTris, src, dst, dFinal, dRank, dHole, dSleft, next);
+        if (nMid)
+            k_level<32><<<nMid, 32, 0, st>>>(dList[cur][1], dNodes, dTris, src, dst, dFinal, dRank, dHole, dSleft, next);
         if (nSmall)
-            k_level_small<<<grid_for(nSmall, 128), 128, 0, st>>>(dListSmall + smallOff, (int)nSmall, dNodes, dTris, src, dst, dFinal,
-                                                                 nextBig, nextSmall, dCounters);
-        ctx->launches += (nBig ? 1 : 0) + (nSmall ? 1 : 0);
-        uint32_t next[2] = {0, 0};
-        BCK(cudaMemcpyAsync(next, dCounters + 1, 8, cudaMemcpyDeviceToHost, st));
+            k_level_small<<<grid_for(nSmall, 128), 128, 0, st>>>(dList[cur][0], (int)nSmall, dNodes, dTris, src, dst, dFinal, next);
+        ctx->launches += (nBig ? 1 : 0) + (nMid ? 1 : 0) + (nSmall ? 1 : 0);
+        BCK(cudaMemcpyAsync(cnt, dCounters, 20, cudaMemcpyDeviceToHost, st));
         BCK(cudaStreamSynchronize(st));
-        if (verbose) fprintf(stderr, "[uvrt_build_bvh] level %2zu: %8u big %8u small ", levels.size() - 1, nBig, nSmall);
+        if (verbose) fprintf(stderr, "[uvrt_build_bvh] level %2zu: %6u huge %7u big %8u mid %8u small ", levels.size() - 1, nHuge, nBig, nMid, nSmall);
         phase("");
-        bigOff += nBig;
-        smallOff += nSmall;
-        nBig = next[0];
-        nSmall = next[1];
+        cur = 1 - cur;
         std::swap(src, dst);
     }
-    uint32_t nTemp = 0;
-    BCK(cudaMemcpyAsync(&nTemp, dCounters, 4, cudaMemcpyDeviceToHost, st));
-    BCK(cudaStreamSynchronize(st));
+    const uint32_t nTemp = cnt[0];
     // renumber: subtree sizes bottom-up, reference indices top-down
     for (int d = (int)levels.size() - 1; d >= 0; d--) {
         const Level& lv = levels[d];
-        if (lv.nBig) k_sizes<<<grid_for(lv.nBig, 256), 256, 0, st>>>(dList + lv.bigOff, (int)lv.nBig, dNodes, dAux);
-        if (lv.nSmall) k_sizes<<<grid_for(lv.nSmall, 256), 256, 0, st>>>(dListSmall + lv.smallOff, (int)lv.nSmall, dNodes, dAux);
+        k_sizes<<<grid_for(lv.idEnd - lv.idBegin, 256), 256, 0, st>>>(lv.idBegin, (int)(lv.idEnd - lv.idBegin), dNodes, dAux);
     }
     k_number_top<<<1, 1, 0, st>>>(dNodes, dAux, dUsed);
     for (size_t d = 4; d < levels.size(); d++) {
         const Level& lv = levels[d];
-        if (lv.nBig) k_number_level<<<grid_for(lv.nBig, 256), 256, 0, st>>>(dList + lv.bigOff, (int)lv.nBig, dNodes, dAux);
-        if (lv.nSmall) k_number_level<<<grid_for(lv.nSmall, 256), 256, 0, st>>>(dListSmall + lv.smallOff, (int)lv.nSmall, dNodes, dAux);
+        k_number_level<<<grid_for(lv.idEnd - lv.idBegin, 256), 256, 0, st>>>(lv.idBegin, (int)(lv.idEnd - lv.idBegin), dNodes, dAux);
     }
     k_emit<<<grid_for(nTemp, 256), 256, 0, st>>>(dNodes, dAux, (int)nTemp, dOut);
-    ctx->launches += (int64_t)levels.size() * 4 + 2;
+    ctx->launches += (int64_t)levels.size() * 2 + 2;
     uint32_t used = 0;
     BCK(cudaMemcpyAsync(&used, dUsed, 4, cudaMemcpyDeviceToHost, st));
     BCK(cudaStreamSynchronize(st));

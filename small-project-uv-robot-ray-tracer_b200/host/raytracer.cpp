@@ -141,7 +141,10 @@ void RayTracer::ComputeSingleLightDosageMap(LightPos lightPos, int photonsPerLig
     }
     seedState = SeedAfter(lightposition);
     launchCounter++;
-    photonMapSize += photonsPerLight;
+    // the reference's `int photonMapSize` (raytracer.h:56) overflows after 2^31 photons (64 default
+    // iterations): count in 64 bits and let the int field saturate instead of wrapping
+    photonMapSizeTotal += photonsPerLight;
+    photonMapSize = photonMapSizeTotal > 0x7fffffffLL ? 0x7fffffff : (int)photonMapSizeTotal;
 }
 
 // Photon counts -> dose or irradiance -> heat-map colours (raytracer.cpp:93-120)
@@ -154,7 +157,8 @@ void RayTracer::Shade()
         Check(uvrt_color(ctx, minPower, thresholdView), "color");
     } else {
         // every photon carries 1/(photons per light) of one lamp's power; x0.1: J/m^2 -> mJ/cm^2
-        int perLight = lightPositions.empty() ? 0 : photonMapSize / (int)lightPositions.size();
+        long long perLight64 = lightPositions.empty() ? 0 : photonMapSizeTotal / (long long)lightPositions.size();
+        int perLight = perLight64 > 0x7fffffffLL ? 0x7fffffff : (int)perLight64;
         if (!Check(uvrt_shade(ctx, 0, perLight, lightIntensity * 0.1f), "shade")) return;
         Check(uvrt_color(ctx, minDosage, thresholdView), "color");
     }
@@ -195,6 +199,7 @@ void RayTracer::ResetDosageMap()
 void RayTracer::ClearBuffers(bool resetColor)
 {
     photonMapSize = 0;
+    photonMapSizeTotal = 0;
     if (!ok) return;
     // the reference also reallocates its 32*photonCount-byte ray buffer here (raytracer.cpp:137);
     // the backend sizes its ray buffer by the largest launch instead
@@ -248,6 +253,7 @@ void RayTracer::CalibratePower(float measurePower, float measureHeight, float me
     }
     UploadScene();             // back to the room (per-triangle buffers are zeroed)
     photonMapSize = 0;
+    photonMapSizeTotal = 0;
     std::cout << "Done calibrating " << std::endl;
 }
 

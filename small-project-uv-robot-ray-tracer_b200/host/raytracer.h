@@ -73,6 +73,7 @@ public:
     // k % shardCount == shardRank; every rank advances seedState and photonMapSize for every launch.
     int shardRank = 0, shardCount = 1;
     long long launchCounter = 0;
+    long long photonMapSizeTotal = 0;   // photonMapSize without the int overflow (see ComputeSingleLightDosageMap)
     // Cross-rank sum (photon map) and max (max map); needs uvrt_comm_init on ctx.  Call once,
     // after the last ComputeDosageMap() and before Shade().
     void Reduce();
