@@ -38,7 +38,8 @@ typedef enum uvrt_status {
     UVRT_ERR_NO_SCENE = -3,  /* a stage was launched before uvrt_upload_scene */
     UVRT_ERR_NCCL = -4,      /* NCCL missing or failed */
     UVRT_ERR_NO_MEMORY = -5, /* host or device allocation failed */
-    UVRT_ERR_NO_DEVICE = -6  /* no CUDA device / driver: the backend cannot run (no fallback) */
+    UVRT_ERR_NO_DEVICE = -6, /* no CUDA device / driver: the backend cannot run (no fallback) */
+    UVRT_ERR_IO = -7         /* a file could not be read or written (host layer) */
 } uvrt_status;
 
 /* Device buffers addressable through uvrt_read / uvrt_write.  Names follow raytracer.h:54-55. */
@@ -48,7 +49,9 @@ typedef enum uvrt_buffer {
     UVRT_BUF_SUM = 2,    /* photonMapBuffer:     nTris x f64  sum of count x duration             */
     UVRT_BUF_MAX = 3,    /* maxPhotonMapBuffer:  nTris x f64  max per-launch count                */
     UVRT_BUF_DOSE = 4,   /* dosageBuffer:        nTris x f32                                      */
-    UVRT_BUF_COLOR = 5   /* colorBuffer:         nTris x 9 x f32 (plain buffer instead of GL VBO) */
+    UVRT_BUF_COLOR = 5,  /* colorBuffer:         nTris x 9 x f32 (plain buffer instead of GL VBO) */
+    UVRT_BUF_PAIRS = 6,  /* diagnostic, read only: traversal layout, 64 B per inner node   */
+    UVRT_BUF_WTRIS = 7   /* diagnostic, read only: leaf-ordered triangles, 64 B per slot                  */
 } uvrt_buffer;
 
 /* Stage ids for uvrt_stage_time */

@@ -81,6 +81,13 @@ int uvrt_sim_read_dose(uvrt_sim* sim, float* dst, int capacity);
 /* Work sharing over ranks (launch k goes to rank k % count) and the final cross-rank reduction. */
 int uvrt_sim_set_shard(uvrt_sim* sim, int rank, int count);
 int uvrt_sim_reduce(uvrt_sim* sim);
+/* Result export: <basePath>.dose.f32 (float32 per triangle), .ply (per-vertex colours of dosageToColor),
+ * .json (parameters).  Call after uvrt_sim_shade / uvrt_sim_run. */
+int uvrt_sim_save_dosage_map(uvrt_sim* sim, const char* basePath);
+/* Checkpoint / resume: photon and max maps, counters and the SEED chain.  load_checkpoint replaces
+ * ResetDosageMap at the start of a resumed run; continue with uvrt_sim_tick. */
+int uvrt_sim_save_checkpoint(uvrt_sim* sim, const char* path);
+int uvrt_sim_load_checkpoint(uvrt_sim* sim, const char* path);
 /* The backend context behind the RayTracer (valid after uvrt_sim_init), for uvrt_read & co. */
 uvrt_ctx* uvrt_sim_ctx(uvrt_sim* sim);
 int64_t uvrt_sim_rays_traced(const uvrt_sim* sim);

@@ -20,7 +20,7 @@ class UvrtError(RuntimeError):
 
 
 class BUF:
-    RAYS, COUNTS, SUM, MAX, DOSE, COLOR = range(6)
+    RAYS, COUNTS, SUM, MAX, DOSE, COLOR, PAIRS, WTRIS = range(8)
 
 
 class STAGE:
@@ -156,6 +156,9 @@ def host():
         "uvrt_sim_run": (i, [vp, vp, i]),
         "uvrt_sim_calibrate": (i, [vp, f, f, f, C.POINTER(f)]),
         "uvrt_sim_read_dose": (i, [vp, vp, i]),
+        "uvrt_sim_save_dosage_map": (i, [vp, C.c_char_p]),
+        "uvrt_sim_save_checkpoint": (i, [vp, C.c_char_p]),
+        "uvrt_sim_load_checkpoint": (i, [vp, C.c_char_p]),
         "uvrt_sim_set_shard": (i, [vp, i, i]),
         "uvrt_sim_reduce": (i, [vp]),
         "uvrt_sim_ctx": (vp, [vp]),
@@ -278,6 +281,10 @@ class Context:
             out = np.zeros(n, dtype=np.float64)
         elif what == BUF.DOSE:
             out = np.zeros(n, dtype=np.float32)
+        elif what == BUF.PAIRS:
+            out = np.zeros((max(self.scene_info()["inner"], 1), 16), dtype=np.uint32)
+        elif what == BUF.WTRIS:
+            out = np.zeros((n_rays if n_rays is not None else n, 16), dtype=np.uint32)
         else:
             out = np.zeros((n, 9), dtype=np.float32)
         self.check(self.L.uvrt_read(self.h, what, _p(out), out.nbytes))
@@ -465,6 +472,15 @@ class Sim:
         out = C.c_float()
         self.check(self.H.uvrt_sim_calibrate(self.h, measure_power, measure_height, measure_dist, C.byref(out)))
         return out.value
+
+    def save_dosage_map(self, base_path):
+        self.check(self.H.uvrt_sim_save_dosage_map(self.h, str(base_path).encode()))
+
+    def save_checkpoint(self, path):
+        self.check(self.H.uvrt_sim_save_checkpoint(self.h, str(path).encode()))
+
+    def load_checkpoint(self, path):
+        self.check(self.H.uvrt_sim_load_checkpoint(self.h, str(path).encode()))
 
     def read_dose(self):
         n = self.mesh_info()["triangles"]

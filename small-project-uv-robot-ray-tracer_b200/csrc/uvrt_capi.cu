@@ -5,6 +5,7 @@
 #include "../../include/uvrt.h"
 #include "uvrt_kernels.cuh"
 #include "uvrt_bvh_build.cuh"
+#include "uvrt_scene_prep.cuh"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -91,6 +92,7 @@ struct RaySlot {
     uint2* dKeyRank = nullptr;
     uint32_t* dPerm = nullptr;
     long long permCap = 0;
+    long long permRays = -1;             // dPerm already holds the permutation of this many rays (pipelined trace)
     float binY0 = 0.0f, binLen = 1.0f;   // lamp extent of the rays in the buffer
     bool binExtentKnown = false;
     cudaEvent_t genDone = nullptr, freeEv = nullptr;
@@ -106,6 +108,7 @@ struct uvrt_ctx {
     // scene (device layout, DESIGN.md "Data layout in HBM")
     int nTris = 0;
     int nPairs = 0, nLeaves = 0, depth = 0;
+    long long nSlots = 0;                // leaf triangle slots (= nTris for a tree that covers the mesh)
     uint32_t rootRef = 0;
     int sceneTame = 0;
     cudaTextureObject_t pairsTex = 0;   // the same buffer as a 1-D float4 texture ("fetch_mode" experiment)
@@ -141,6 +144,16 @@ struct uvrt_ctx {
     size_t pairCap = 0, wtriCap = 0;     // device capacities in bytes
     std::vector<int32_t> upId;
     std::vector<uint32_t> upOrder;
+    // device-side repack (uvrt_scene_prep.cuh): raw reference arrays + per-node scratch
+    int hostRepack = 0;                  // option "host_repack": 1 = repack on the host cores instead
+    void* dRawNodes = nullptr;
+    uint32_t* dRawIdx = nullptr;
+    unsigned long long* dPrepQueue = nullptr;
+    uint32_t* dPrepNode = nullptr;       // parent, arrive, subInner, subSlots: 4 x nodeCap
+    void* dPrepStatus = nullptr;
+    void* hPrepStatus = nullptr;         // pinned
+    size_t prepNodeCap = 0, prepTriCap = 0;
+    int prepBlocks = 0;
 
     // options
     int extendVariant = -1;   // -1: default
@@ -180,6 +193,12 @@ int fail(uvrt_ctx* c, int code, const char* fmt, ...)
         if (e_ != cudaSuccess)                                                                \
             return fail(ctx, e_ == cudaErrorMemoryAllocation ? UVRT_ERR_NO_MEMORY : UVRT_ERR_CUDA, \
                         "%s failed: %s", #call, cudaGetErrorString(e_));                      \
+    } while (0)
+
+#define CK_LAUNCH(name)                                                                    \
+    do {                                                                                   \
+        cudaError_t e_ = cudaGetLastError();                                               \
+        if (e_ != cudaSuccess) return fail(ctx, UVRT_ERR_CUDA, "%s launch failed: %s", name, cudaGetErrorString(e_)); \
     } while (0)
 
 struct Bind {
@@ -260,6 +279,8 @@ int check_buffer(uvrt_ctx* ctx, uvrt_buffer what, void** ptr, size_t* bytes)
     case UVRT_BUF_MAX: *ptr = ctx->dMax; *bytes = n * 8; return UVRT_OK;
     case UVRT_BUF_DOSE: *ptr = ctx->dDose; *bytes = n * 4; return UVRT_OK;
     case UVRT_BUF_COLOR: *ptr = ctx->dColor; *bytes = n * 36; return UVRT_OK;
+    case UVRT_BUF_PAIRS: *ptr = ctx->dPairs; *bytes = (size_t)std::max(ctx->nPairs, 1) * 64; return UVRT_OK;
+    case UVRT_BUF_WTRIS: *ptr = ctx->dWtris; *bytes = (size_t)ctx->nSlots * 64; return UVRT_OK;
     }
     return fail(ctx, UVRT_ERR_INVALID, "unknown buffer id %d", (int)what);
 }
@@ -382,23 +403,23 @@ int bin_prepare(uvrt_ctx* ctx, long long nRays, BinDims* d)
     return UVRT_OK;
 }
 
-int bin_finish(uvrt_ctx* ctx, long long nRays)
+int bin_finish(uvrt_ctx* ctx, long long nRays, cudaStream_t stream)
 {
-    StageTimer t(ctx, UVRT_STAGE_BIN);
+    StageTimer t(ctx, UVRT_STAGE_BIN, stream);
     if (ctx->rs().countedRays != nRays) {
         // the rays in the buffer did not (all) come from k_generate<1>: count them now
         BinDims d;
         int rc = bin_prepare(ctx, nRays, &d);
         if (rc) return rc;
-        if (ctx->rs().countedRays >= 0) CK(cudaMemsetAsync(ctx->rs().dBinCount, 0, (size_t)ctx->rs().binCap * 4, ctx->stream));
-        k_bin_count<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->rs().dRays, (uint32_t)nRays, d, ctx->rs().dBinCount, ctx->rs().dKeyRank);
+        if (ctx->rs().countedRays >= 0) CK(cudaMemsetAsync(ctx->rs().dBinCount, 0, (size_t)ctx->rs().binCap * 4, stream));
+        k_bin_count<<<grid_for(nRays, 256), 256, 0, stream>>>(ctx->rs().dRays, (uint32_t)nRays, d, ctx->rs().dBinCount, ctx->rs().dKeyRank);
         ctx->launches++;
     }
     ctx->rs().countedRays = -1;
     const int nScanBlocks = ctx->rs().binUsed / kBinsPerScanBlock;
-    k_bin_scan<<<nScanBlocks, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(ctx->rs().dBinCount),
+    k_bin_scan<<<nScanBlocks, 256, 0, stream>>>(reinterpret_cast<uint4*>(ctx->rs().dBinCount),
                                                      reinterpret_cast<uint4*>(ctx->rs().dBinStart), ctx->rs().dBinBlock);
-    k_bin_scatter<<<grid_for(nRays, 256), 256, 0, ctx->stream>>>(ctx->rs().dKeyRank, ctx->rs().dBinStart, ctx->rs().dBinBlock, nScanBlocks,
+    k_bin_scatter<<<grid_for(nRays, 256), 256, 0, stream>>>(ctx->rs().dKeyRank, ctx->rs().dBinStart, ctx->rs().dBinBlock, nScanBlocks,
                                                                  (uint32_t)nRays, ctx->rs().dPerm);
     ctx->launches += 2;
     return UVRT_OK;
@@ -498,7 +519,9 @@ void uvrt_destroy(uvrt_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     void* ptrs[] = {ctx->dPairs, ctx->dWtris, ctx->dVerts, ctx->dCounts, ctx->dSum, ctx->dMax, ctx->dDose,
-                    ctx->dColor, ctx->dQueue, ctx->dSeeds, ctx->dSeedPos, ctx->dFlush};
+                    ctx->dColor, ctx->dQueue, ctx->dSeeds, ctx->dSeedPos, ctx->dFlush, ctx->dRawNodes, ctx->dRawIdx,
+                    ctx->dPrepQueue, ctx->dPrepNode, ctx->dPrepStatus};
+    if (ctx->hPrepStatus) cudaFreeHost(ctx->hPrepStatus);
     for (void* p : ptrs) if (p) cudaFree(p);
     for (RaySlot& r : ctx->slots) {
         void* q[] = {r.dRays, r.dBinCount, r.dBinStart, r.dBinBlock, r.dKeyRank, r.dPerm};
@@ -528,13 +551,169 @@ int uvrt_device_info(uvrt_ctx* ctx, char* dst, size_t bytes, int* smCount, int* 
     return UVRT_OK;
 }
 
-int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* nodesV, int nNodes,
-                      const uint32_t* triIdx)
+// device buffers of the traversal layout and the per-triangle state
+static int ensure_scene_buffers(uvrt_ctx* ctx, size_t pairBytes, size_t wtriBytes, int nTris)
 {
-    if (!ctx) return UVRT_ERR_INVALID;
-    if (!trisV || !nodesV || !triIdx || nTris <= 0 || nNodes <= 0)
-        return fail(ctx, UVRT_ERR_INVALID, "upload_scene: null pointer or empty scene (nTris=%d nNodes=%d)", nTris, nNodes);
-    Bind b(ctx);
+    int rc;
+    if (pairBytes > ctx->pairCap) {
+        ctx->pairCap = 0;
+        if (ctx->pairsTex) { cudaDestroyTextureObject(ctx->pairsTex); ctx->pairsTex = 0; }
+        if ((rc = dev_alloc(ctx, &ctx->dPairs, pairBytes / 16))) return rc;
+        ctx->pairCap = pairBytes;
+        if (pairBytes / 16 <= (1u << 27)) {
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = ctx->dPairs;
+            rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+            rd.res.linear.sizeInBytes = pairBytes;
+            cudaTextureDesc td{};
+            td.readMode = cudaReadModeElementType;
+            if (cudaCreateTextureObject(&ctx->pairsTex, &rd, &td, nullptr) != cudaSuccess) { ctx->pairsTex = 0; cudaGetLastError(); }
+        }
+    }
+    if (wtriBytes > ctx->wtriCap) {
+        ctx->wtriCap = 0;
+        if ((rc = dev_alloc(ctx, &ctx->dWtris, wtriBytes / 16))) return rc;
+        ctx->wtriCap = wtriBytes;
+    }
+    if (nTris != ctx->nTris) {
+        ctx->nTris = 0;
+        if ((rc = dev_alloc(ctx, &ctx->dVerts, (size_t)nTris * 4))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->dCounts, (size_t)nTris))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->dSum, (size_t)nTris))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->dMax, (size_t)nTris))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->dDose, (size_t)nTris))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->dColor, (size_t)nTris * 9))) return rc;
+        ctx->nTris = nTris;
+        CK(cudaMemsetAsync(ctx->dCounts, 0, (size_t)nTris * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->dSum, 0, (size_t)nTris * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->dMax, 0, (size_t)nTris * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->dDose, 0, (size_t)nTris * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->dColor, 0, (size_t)nTris * 36, ctx->stream));
+    }
+    return UVRT_OK;
+}
+
+static int ensure_stage(uvrt_ctx* ctx, size_t total)
+{
+    if (ctx->hStageBytes < total) {
+        if (ctx->hStage) cudaFreeHost(ctx->hStage);
+        ctx->hStage = nullptr;
+        ctx->hStageBytes = 0;
+        CK(cudaMallocHost(&ctx->hStage, total));
+        ctx->hStageBytes = total;
+    }
+    return UVRT_OK;
+}
+
+// memcpy spread over the host cores (the staging copy of a 1 GB scene is otherwise the slowest step)
+static void par_copy(void* dst, const void* src, size_t bytes)
+{
+    const size_t chunk = 1u << 20;
+    const long long nChunks = (long long)((bytes + chunk - 1) / chunk);
+#pragma omp parallel for schedule(static) if (nChunks > 2)
+    for (long long c = 0; c < nChunks; c++) {
+        const size_t off = (size_t)c * chunk;
+        memcpy((char*)dst + off, (const char*)src + off, std::min(chunk, bytes - off));
+    }
+}
+
+// The repack on the device (uvrt_scene_prep.cuh): the reference's three arrays go up as they are.
+static int upload_scene_device(uvrt_ctx* ctx, const void* trisV, int nTris, const void* nodesV, int nNodes, const uint32_t* triIdx)
+{
+    using namespace uvrt_prep;
+    const size_t nodeBytes = (size_t)nNodes * 32, idxBytes = (size_t)nTris * 4, vertBytes = (size_t)nTris * 64;
+    const size_t idxOff = (nodeBytes + 255) & ~(size_t)255, vertOff = (idxOff + idxBytes + 255) & ~(size_t)255;
+    int rc = ensure_stage(ctx, vertOff + vertBytes);
+    if (rc) return rc;
+    if ((size_t)nNodes > ctx->prepNodeCap) {
+        ctx->prepNodeCap = 0;
+        void* old[] = {ctx->dRawNodes, ctx->dPrepQueue, ctx->dPrepNode};
+        for (void* p : old) if (p) cudaFree(p);
+        ctx->dRawNodes = nullptr; ctx->dPrepQueue = nullptr; ctx->dPrepNode = nullptr;
+        CK(cudaMalloc(&ctx->dRawNodes, nodeBytes));
+        CK(cudaMalloc((void**)&ctx->dPrepQueue, (size_t)nNodes * 8));
+        CK(cudaMalloc((void**)&ctx->dPrepNode, (size_t)nNodes * 16));
+        ctx->prepNodeCap = (size_t)nNodes;
+    }
+    if ((size_t)nTris > ctx->prepTriCap) {
+        ctx->prepTriCap = 0;
+        if (ctx->dRawIdx) cudaFree(ctx->dRawIdx);
+        ctx->dRawIdx = nullptr;
+        CK(cudaMalloc((void**)&ctx->dRawIdx, idxBytes));
+        ctx->prepTriCap = (size_t)nTris;
+    }
+    if (!ctx->dPrepStatus) {
+        CK(cudaMalloc(&ctx->dPrepStatus, sizeof(Status)));
+        CK(cudaMallocHost(&ctx->hPrepStatus, sizeof(Status)));
+        int perSm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_prep_walk, 128, 0));
+        ctx->prepBlocks = std::max(1, std::min(perSm, 8)) * ctx->prop.multiProcessorCount;   // all blocks resident
+    }
+    cudaStream_t st = ctx->stream;
+    char* stage = (char*)ctx->hStage;
+    Status* dSt = (Status*)ctx->dPrepStatus;
+    Status* hSt = (Status*)ctx->hPrepStatus;
+    uint32_t* parent = ctx->dPrepNode;
+    uint32_t *arrive = parent + (size_t)ctx->prepNodeCap, *subInner = arrive + (size_t)ctx->prepNodeCap,
+             *subSlots = subInner + (size_t)ctx->prepNodeCap;
+    // nodes + triIdx first: the tree walk needs nothing else and runs while the triangles are staged
+    par_copy(stage, nodesV, nodeBytes);
+    par_copy(stage + idxOff, triIdx, idxBytes);
+    CK(cudaMemcpyAsync(ctx->dRawNodes, stage, nodeBytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->dRawIdx, stage + idxOff, idxBytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->dPrepQueue, 0xff, (size_t)nNodes * 8, st));
+    CK(cudaMemsetAsync(parent, 0xff, (size_t)nNodes * 4, st));
+    CK(cudaMemsetAsync(arrive, 0, (size_t)nNodes * 4, st));
+    k_prep_init<<<1, 1, 0, st>>>(ctx->dPrepQueue, dSt, parent);
+    const int blocks = (int)std::min<long long>(ctx->prepBlocks, ((long long)nNodes + 127) / 128);
+    k_prep_walk<<<blocks, 128, 0, st>>>((const RawNode*)ctx->dRawNodes, (uint32_t)nNodes, ctx->dRawIdx, (uint32_t)nTris, kStack,
+                                        ctx->dPrepQueue, parent, arrive, subInner, subSlots, dSt);
+    CK(cudaMemcpyAsync(hSt, dSt, sizeof(Status), cudaMemcpyDeviceToHost, st));
+    ctx->launches += 2;
+    par_copy(stage + vertOff, trisV, vertBytes);
+    CK(cudaStreamSynchronize(st));
+    CK_LAUNCH("scene walk");
+    const Status s = *hSt;
+    switch (s.err) {
+    case PREP_OK: break;
+    case PREP_NODE_RANGE:
+        return fail(ctx, UVRT_ERR_INVALID,
+                    "upload_scene: node %u is reachable but nNodes is %d (the reference's nodesUsed = 2N "
+                    "truncates its own tree; pass the full array)", s.errA, nNodes);
+    case PREP_TWICE: return fail(ctx, UVRT_ERR_INVALID, "upload_scene: node %u reached twice", s.errA);
+    case PREP_LEAF_SPAN:
+        return fail(ctx, UVRT_ERR_INVALID, "upload_scene: leaf %u spans triIdx[%u..%u) of %d", s.errA, s.errB, s.errC, nTris);
+    case PREP_TRI_RANGE: return fail(ctx, UVRT_ERR_INVALID, "upload_scene: triIdx value %u out of range", s.errA);
+    case PREP_DEPTH: return fail(ctx, UVRT_ERR_INVALID, "upload_scene: BVH depth %u exceeds the traversal stack (%d)", s.errA, kStack);
+    default: return fail(ctx, UVRT_ERR_CUDA, "upload_scene: the device tree walk did not finish (code %u at queue entry %u)", s.err, s.errA);
+    }
+    if (!s.done) return fail(ctx, UVRT_ERR_CUDA, "upload_scene: the device tree walk ended without reaching the root");
+    const int nPairs = (int)s.nPairs;
+    const unsigned long long nSlots = s.nSlots;
+    const size_t pairBytes = (size_t)std::max(nPairs, 1) * 64, wtriBytes = (size_t)std::max<unsigned long long>(nSlots, 1) * 64;
+    if ((rc = ensure_scene_buffers(ctx, pairBytes, wtriBytes, nTris))) return rc;
+    CK(cudaMemcpyAsync(ctx->dVerts, stage + vertOff, vertBytes, cudaMemcpyHostToDevice, st));
+    if (nPairs == 0) CK(cudaMemsetAsync(ctx->dPairs, 0, pairBytes, st));
+    const uint32_t reachable = s.tail;
+    k_prep_emit<<<grid_for(reachable, 256), 256, 0, st>>>((const RawNode*)ctx->dRawNodes, ctx->dRawIdx, ctx->dVerts, ctx->dPrepQueue,
+                                                         reachable, parent, subInner, subSlots, ctx->dPairs, ctx->dWtris, dSt);
+    CK(cudaMemcpyAsync(hSt, dSt, sizeof(Status), cudaMemcpyDeviceToHost, st));
+    ctx->launches += 1;
+    CK(cudaStreamSynchronize(st));   // the staging buffer may be reused right away
+    CK_LAUNCH("scene emit");
+    ctx->nPairs = nPairs;
+    ctx->nLeaves = nPairs + 1;       // a binary tree
+    ctx->nSlots = (long long)nSlots;
+    ctx->depth = (int)s.maxDepth;
+    ctx->sceneTame = hSt->tame ? 1 : 0;
+    ctx->rootRef = s.rootIsLeaf ? kLeafFlag : 0u;
+    ctx->uploadBytes = (int64_t)(nodeBytes + idxBytes + vertBytes);
+    return UVRT_OK;
+}
+
+static int upload_scene_host(uvrt_ctx* ctx, const void* trisV, int nTris, const void* nodesV, int nNodes, const uint32_t* triIdx)
+{
     const HostTri* tris = (const HostTri*)trisV;
     const HostNode* nodes = (const HostNode*)nodesV;
 
@@ -583,12 +762,9 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
     size_t pairBytes = (size_t)std::max(nPairs, 1) * 64, wtriBytes = (size_t)std::max<long long>(nSlots, 1) * 64,
            vertBytes = (size_t)nTris * 64;
     size_t total = pairBytes + wtriBytes + vertBytes;
-    if (ctx->hStageBytes < total) {
-        if (ctx->hStage) cudaFreeHost(ctx->hStage);
-        ctx->hStage = nullptr;
-        ctx->hStageBytes = 0;
-        CK(cudaMallocHost(&ctx->hStage, total));
-        ctx->hStageBytes = total;
+    {
+        int rcs = ensure_stage(ctx, total);
+        if (rcs) return rcs;
     }
     float* hp = (float*)ctx->hStage;
     float* hw = (float*)((char*)ctx->hStage + pairBytes);
@@ -640,52 +816,32 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
 
     // ---- device buffers -------------------------------------------------------------------------
     int rc;
-    if (pairBytes > ctx->pairCap) {
-        ctx->pairCap = 0;
-        if (ctx->pairsTex) { cudaDestroyTextureObject(ctx->pairsTex); ctx->pairsTex = 0; }
-        if ((rc = dev_alloc(ctx, &ctx->dPairs, pairBytes / 16))) return rc;
-        ctx->pairCap = pairBytes;
-        if (pairBytes / 16 <= (1u << 27)) {
-            cudaResourceDesc rd{};
-            rd.resType = cudaResourceTypeLinear;
-            rd.res.linear.devPtr = ctx->dPairs;
-            rd.res.linear.desc = cudaCreateChannelDesc<float4>();
-            rd.res.linear.sizeInBytes = pairBytes;
-            cudaTextureDesc td{};
-            td.readMode = cudaReadModeElementType;
-            if (cudaCreateTextureObject(&ctx->pairsTex, &rd, &td, nullptr) != cudaSuccess) { ctx->pairsTex = 0; cudaGetLastError(); }
-        }
-    }
-    if (wtriBytes > ctx->wtriCap) {
-        ctx->wtriCap = 0;
-        if ((rc = dev_alloc(ctx, &ctx->dWtris, wtriBytes / 16))) return rc;
-        ctx->wtriCap = wtriBytes;
-    }
-    if (nTris != ctx->nTris) {
-        if ((rc = dev_alloc(ctx, &ctx->dVerts, (size_t)nTris * 4))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->dCounts, (size_t)nTris))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->dSum, (size_t)nTris))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->dMax, (size_t)nTris))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->dDose, (size_t)nTris))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->dColor, (size_t)nTris * 9))) return rc;
-        ctx->nTris = nTris;
-        CK(cudaMemsetAsync(ctx->dCounts, 0, (size_t)nTris * 4, ctx->stream));
-        CK(cudaMemsetAsync(ctx->dSum, 0, (size_t)nTris * 8, ctx->stream));
-        CK(cudaMemsetAsync(ctx->dMax, 0, (size_t)nTris * 8, ctx->stream));
-        CK(cudaMemsetAsync(ctx->dDose, 0, (size_t)nTris * 4, ctx->stream));
-        CK(cudaMemsetAsync(ctx->dColor, 0, (size_t)nTris * 36, ctx->stream));
-    }
+    if ((rc = ensure_scene_buffers(ctx, pairBytes, wtriBytes, nTris))) return rc;
     CK(cudaMemcpyAsync(ctx->dPairs, hp, pairBytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dWtris, hw, wtriBytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dVerts, hv, vertBytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // the staging buffer may be reused right away
     ctx->nPairs = nPairs;
     ctx->nLeaves = nLeaves;
+    ctx->nSlots = nSlots;
     ctx->depth = depth;
     ctx->sceneTame = tame ? 1 : 0;
     ctx->rootRef = child_ref(0);
     ctx->uploadBytes = (int64_t)total;
     return UVRT_OK;
+}
+
+int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* nodesV, int nNodes,
+                      const uint32_t* triIdx)
+{
+    if (!ctx) return UVRT_ERR_INVALID;
+    if (!trisV || !nodesV || !triIdx || nTris <= 0 || nNodes <= 0)
+        return fail(ctx, UVRT_ERR_INVALID, "upload_scene: null pointer or empty scene (nTris=%d nNodes=%d)", nTris, nNodes);
+    Bind b(ctx);
+    // rays of a pipelined launch may still be in flight on the second stream
+    if (ctx->genStream) CK(cudaStreamSynchronize(ctx->genStream));
+    return ctx->hostRepack ? upload_scene_host(ctx, trisV, nTris, nodesV, nNodes, triIdx)
+                           : upload_scene_device(ctx, trisV, nTris, nodesV, nNodes, triIdx);
 }
 
 // ---- device BVH build (uvrt_bvh_build.cuh) ----------------------------------------------------------
@@ -861,12 +1017,6 @@ int uvrt_scene_info(uvrt_ctx* ctx, int* innerNodes, int* leaves, int* depth, int
     if (!ctx->nTris) return fail(ctx, UVRT_ERR_NO_SCENE, "%s: no scene uploaded", __func__); \
     Bind bind_(ctx)
 
-#define CK_LAUNCH(name)                                                                    \
-    do {                                                                                   \
-        cudaError_t e_ = cudaGetLastError();                                               \
-        if (e_ != cudaSuccess) return fail(ctx, UVRT_ERR_CUDA, "%s launch failed: %s", name, cudaGetErrorString(e_)); \
-    } while (0)
-
 int uvrt_reset(uvrt_ctx* ctx, int resetColor)
 {
     NEED_SCENE();
@@ -890,6 +1040,7 @@ static int generate_on(uvrt_ctx* ctx, cudaStream_t stream, float lx, float ly, f
     if (rc) return rc;
     RaySlot& S = ctx->rs();
     ctx->lastRays = nRays;
+    S.permRays = -1;
     S.binY0 = ly;
     S.binLen = lightLength;
     S.binExtentKnown = true;
@@ -934,15 +1085,18 @@ int uvrt_extend(uvrt_ctx* ctx, int64_t nRays)
     const uint32_t* perm = nullptr;
     // a few thousand rays are not worth the extra launches
     if (ctx->binRays && nRays >= kMinRaysForBinning) {
-        rc = bin_finish(ctx, nRays);
-        if (rc) return rc;
-        CK_LAUNCH("bin");
+        if (ctx->rs().permRays != nRays) {          // not already done on the generate stream
+            rc = bin_finish(ctx, nRays, ctx->stream);
+            if (rc) return rc;
+            CK_LAUNCH("bin");
+        }
         perm = ctx->rs().dPerm;
     } else if (ctx->rs().countedRays >= 0) {
         // binning was switched off between generate and extend: drop the slots generate took
         CK(cudaMemsetAsync(ctx->rs().dBinCount, 0, (size_t)ctx->rs().binCap * 4, ctx->stream));
         ctx->rs().countedRays = -1;
     }
+    ctx->rs().permRays = -1;
     {
         StageTimer t(ctx, UVRT_STAGE_EXTEND);
         rc = launch_extend(ctx, nRays, perm);
@@ -981,6 +1135,13 @@ int uvrt_trace_counts(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLe
     if (S.inFlight) CK(cudaStreamWaitEvent(ctx->genStream, S.freeEv, 0));   // the extend that last read this slot
     int rc = generate_on(ctx, ctx->genStream, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
     if (rc) return rc;
+    if (ctx->binRays && nRays >= kMinRaysForBinning && S.countedRays == nRays) {
+        // scan + scatter of the ray binning also run ahead, next to the previous launch's extend
+        rc = bin_finish(ctx, nRays, ctx->genStream);
+        if (rc) return rc;
+        CK_LAUNCH("bin");
+        S.permRays = nRays;
+    }
     CK(cudaEventRecord(S.genDone, ctx->genStream));
     CK(cudaStreamWaitEvent(ctx->stream, S.genDone, 0));
     rc = uvrt_extend(ctx, nRays);
@@ -1065,6 +1226,8 @@ int uvrt_read(uvrt_ctx* ctx, uvrt_buffer what, void* dst, size_t bytes)
 int uvrt_write(uvrt_ctx* ctx, uvrt_buffer what, const void* src, size_t bytes)
 {
     NEED_SCENE();
+    if (what == UVRT_BUF_PAIRS || what == UVRT_BUF_WTRIS)
+        return fail(ctx, UVRT_ERR_INVALID, "write: buffer %d is read only (set by uvrt_upload_scene)", (int)what);
     if (what == UVRT_BUF_RAYS) {
         int rc = ensure_rays(ctx, (long long)((bytes + 31) / 32));
         if (rc) return rc;
@@ -1156,6 +1319,7 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
     else if (!strcmp(key, "refill")) ctx->refill = value;
     else if (!strcmp(key, "simple_cfg")) ctx->simpleCfg = value;
     else if (!strcmp(key, "pipeline")) ctx->pipeline = value;
+    else if (!strcmp(key, "host_repack")) ctx->hostRepack = value;
     else if (!strcmp(key, "fetch_mode")) ctx->fetchMode = value;
     else if (!strncmp(key, "bin_", 4)) {
         if (!strcmp(key, "bin_rays")) ctx->binRays = value;
@@ -1185,6 +1349,7 @@ int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value)
     else if (!strcmp(key, "refill")) *value = ctx->refill;
     else if (!strcmp(key, "simple_cfg")) *value = ctx->simpleCfg;
     else if (!strcmp(key, "pipeline")) *value = ctx->pipeline;
+    else if (!strcmp(key, "host_repack")) *value = ctx->hostRepack;
     else if (!strcmp(key, "fetch_mode")) *value = ctx->fetchMode;
     else if (!strcmp(key, "bin_rays")) *value = ctx->binRays;
     else if (!strcmp(key, "bin_y")) *value = ctx->binY;

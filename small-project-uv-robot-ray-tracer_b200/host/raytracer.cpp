@@ -257,6 +257,131 @@ void RayTracer::CalibratePower(float measurePower, float measureHeight, float me
     std::cout << "Done calibrating " << std::endl;
 }
 
+// ---- result export and checkpoints (no counterpart in the reference) -------------------------------
+bool RayTracer::SaveDosageMap(const char* basePath)
+{
+    if (!ok || !mesh) return false;
+    const int n = mesh->triangleCount;
+    const float* dose = ReadDosageMap();
+    if (!ok) return false;
+    const std::string base(basePath);
+    {
+        std::ofstream f(base + ".dose.f32", std::ios::binary);
+        if (!f) { lastError = "SaveDosageMap: cannot write " + base + ".dose.f32"; return false; }
+        f.write((const char*)dose, sizeof(float) * (size_t)n);
+    }
+    std::vector<float> color((size_t)n * 9);
+    if (!Check(uvrt_read(ctx, UVRT_BUF_COLOR, color.data(), color.size() * sizeof(float)), "read color")) return false;
+    {
+        std::ofstream f(base + ".ply", std::ios::binary);
+        if (!f) { lastError = "SaveDosageMap: cannot write " + base + ".ply"; return false; }
+        f << "ply\nformat binary_little_endian 1.0\ncomment uvrt dose map\n"
+          << "element vertex " << (size_t)n * 3 << "\nproperty float x\nproperty float y\nproperty float z\n"
+          << "property uchar red\nproperty uchar green\nproperty uchar blue\n"
+          << "element face " << n << "\nproperty list uchar int vertex_indices\nend_header\n";
+        std::vector<char> buf;
+        buf.reserve((size_t)n * 3 * 15);
+        auto to8 = [](float c) { c = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c); return (unsigned char)(c * 255.0f + 0.5f); };
+        for (int t = 0; t < n; t++) {
+            const float3_strict* v[3] = {&mesh->triangles[t].vertex0, &mesh->triangles[t].vertex1, &mesh->triangles[t].vertex2};
+            for (int k = 0; k < 3; k++) {
+                const float xyz[3] = {v[k]->x, v[k]->y, v[k]->z};
+                const unsigned char rgb[3] = {to8(color[(size_t)t * 9 + k * 3]), to8(color[(size_t)t * 9 + k * 3 + 1]), to8(color[(size_t)t * 9 + k * 3 + 2])};
+                buf.insert(buf.end(), (const char*)xyz, (const char*)xyz + 12);
+                buf.insert(buf.end(), (const char*)rgb, (const char*)rgb + 3);
+            }
+        }
+        f.write(buf.data(), (std::streamsize)buf.size());
+        buf.clear();
+        for (int t = 0; t < n; t++) {
+            const unsigned char three = 3;
+            const int idx[3] = {3 * t, 3 * t + 1, 3 * t + 2};
+            buf.push_back((char)three);
+            buf.insert(buf.end(), (const char*)idx, (const char*)idx + 12);
+        }
+        f.write(buf.data(), (std::streamsize)buf.size());
+    }
+    {
+        std::ofstream f(base + ".json", std::ios::binary);
+        if (!f) { lastError = "SaveDosageMap: cannot write " + base + ".json"; return false; }
+        f << "{\"room\": \"" << mesh->modelFile << "\", \"triangles\": " << n << ", \"floor_height\": " << uvrt_xml::fmt_float(mesh->floorHeight)
+          << ", \"view\": \"" << (viewMode == maxpower ? "max_irradiance_uW_cm2" : "dose_mJ_cm2") << "\""
+          << ", \"photon_count\": " << photonCount << ", \"photons_per_light\": " << photonsPerLight
+          << ", \"iterations\": " << currIterations << ", \"max_iterations\": " << maxIterations
+          << ", \"photons_traced\": " << photonMapSizeTotal << ", \"seed_state\": " << seedState
+          << ", \"lamp_power\": " << uvrt_xml::fmt_float(lightIntensity) << ", \"lamp_length\": " << uvrt_xml::fmt_float(lightLength)
+          << ", \"lamp_height\": " << uvrt_xml::fmt_float(lightHeight) << ", \"min_dose\": " << uvrt_xml::fmt_float(minDosage)
+          << ", \"min_power\": " << uvrt_xml::fmt_float(minPower) << ", \"threshold_view\": " << (thresholdView ? "true" : "false")
+          << ", \"route\": [";
+        for (size_t i = 0; i < lightPositions.size(); i++)
+            f << (i ? ", " : "") << "[" << uvrt_xml::fmt_float(lightPositions[i].position.x) << ", " << uvrt_xml::fmt_float(lightPositions[i].position.y)
+              << ", " << uvrt_xml::fmt_float(lightPositions[i].duration) << "]";
+        f << "], \"files\": {\"dose\": \"float32 x triangles\", \"ply\": \"3 vertices per triangle, uchar rgb\"}}\n";
+    }
+    return true;
+}
+
+namespace {
+struct CheckpointHeader {
+    char magic[8];            // "UVRTCKP1"
+    int32_t triangles, positions, currIterations, photonsPerLight;
+    int64_t launchCounter, photonMapSizeTotal, raysTraced;
+    uint32_t seedState, pad;
+};
+} // namespace
+
+bool RayTracer::SaveCheckpoint(const char* path)
+{
+    if (!ok || !mesh) return false;
+    const size_t n = (size_t)mesh->triangleCount;
+    std::vector<double> maps(2 * n);
+    if (!Check(uvrt_read(ctx, UVRT_BUF_SUM, maps.data(), n * 8), "read photon map")) return false;
+    if (!Check(uvrt_read(ctx, UVRT_BUF_MAX, maps.data() + n, n * 8), "read max map")) return false;
+    CheckpointHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "UVRTCKP1", 8);
+    h.triangles = (int32_t)n; h.positions = (int32_t)lightPositions.size(); h.currIterations = currIterations;
+    h.photonsPerLight = photonsPerLight; h.launchCounter = launchCounter; h.photonMapSizeTotal = photonMapSizeTotal;
+    h.raysTraced = raysTraced; h.seedState = seedState;
+    std::ofstream f(path, std::ios::binary);
+    if (!f) { lastError = std::string("SaveCheckpoint: cannot write ") + path; return false; }
+    f.write((const char*)&h, sizeof h);
+    f.write((const char*)maps.data(), (std::streamsize)(maps.size() * 8));
+    return (bool)f;
+}
+
+bool RayTracer::LoadCheckpoint(const char* path)
+{
+    if (!ok || !mesh) return false;
+    const size_t n = (size_t)mesh->triangleCount;
+    std::ifstream f(path, std::ios::binary);
+    CheckpointHeader h;
+    if (!f || !f.read((char*)&h, sizeof h) || memcmp(h.magic, "UVRTCKP1", 8) != 0) {
+        lastError = std::string("LoadCheckpoint: not a checkpoint: ") + path;
+        return false;
+    }
+    if ((size_t)h.triangles != n || (size_t)h.positions != lightPositions.size()) {
+        lastError = "LoadCheckpoint: checkpoint belongs to another room or route";
+        return false;
+    }
+    std::vector<double> maps(2 * n);
+    if (!f.read((char*)maps.data(), (std::streamsize)(maps.size() * 8))) { lastError = "LoadCheckpoint: truncated file"; return false; }
+    ClearBuffers(false);
+    if (!Check(uvrt_write(ctx, UVRT_BUF_SUM, maps.data(), n * 8), "write photon map")) return false;
+    if (!Check(uvrt_write(ctx, UVRT_BUF_MAX, maps.data() + n, n * 8), "write max map")) return false;
+    currIterations = h.currIterations;
+    launchCounter = h.launchCounter;
+    photonMapSizeTotal = h.photonMapSizeTotal;
+    photonMapSize = photonMapSizeTotal > 0x7fffffffLL ? 0x7fffffff : (int)photonMapSizeTotal;
+    raysTraced = h.raysTraced;
+    seedState = h.seedState;
+    seedQueue.clear();
+    seedQueueHead = 0;
+    startedComputation = true;
+    finishedComputation = currIterations >= maxIterations;
+    return true;
+}
+
 static std::string RoutePath(const char* fileName)
 {
     return AssetRoot() + "positions/" + fileName + ".xml";

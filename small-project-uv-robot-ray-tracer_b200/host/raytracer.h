@@ -80,6 +80,17 @@ public:
     // Copies the per-triangle dose (after Shade) into dosageMap, resized to triangleCount floats.
     const float* ReadDosageMap();
     int64_t RaysTraced() const { return raysTraced; }
+    // Result export (the reference only ever shows the map in its GL window, myapp.cpp:180-205):
+    //   <base>.dose.f32  per-triangle dose / irradiance, float32, triangle order (after Shade)
+    //   <base>.ply       binary little-endian PLY, 3 vertices per triangle, per-vertex uchar RGB from
+    //                    the colour buffer of dosageToColor (shade.cl:43-71), clamped to [0, 1]
+    //   <base>.json      sidecar: room, parameters, route, rays, iterations, SEED
+    bool SaveDosageMap(const char* basePath);
+    // Checkpoint / resume of a run: photon map and max map (f64), iteration and launch counters, the
+    // photon total and the device SEED chain.  A resumed run continues with the rays the uninterrupted
+    // run would have traced, so the final maps are bit-identical.
+    bool SaveCheckpoint(const char* path);
+    bool LoadCheckpoint(const char* path);
 
 private:
     bool Check(int rc, const char* what);

@@ -11,12 +11,17 @@ using namespace Tmpl8;
 static void usage()
 {
     printf("usage: uvrt_cli [--root DIR] [--room NAME] [--route NAME] [--iterations N] [--photons N]\n"
-           "                [--device D] [--maxpower] [--out dose.f32] [--variant V]\n");
+           "                [--device D] [--maxpower] [--out dose.f32] [--export BASE] [--variant V]\n"
+           "                [--device-bvh] [--checkpoint FILE] [--resume FILE]\n"
+           "  --export BASE      BASE.dose.f32, BASE.ply (per-vertex heat-map colours), BASE.json\n"
+           "  --device-bvh       build the BVH on the GPU (uvrt_build_bvh) instead of on the host cores\n"
+           "  --checkpoint FILE  rewrite FILE after every iteration; --resume FILE continues such a run\n");
 }
 
 int main(int argc, char** argv)
 {
-    std::string room = "testroomopt", route = "route", out;
+    std::string room = "testroomopt", route = "route", out, exportBase, checkpoint, resume;
+    bool deviceBvh = false;
     int iterations = -1, photons = -1, device = 0, variant = -1;
     bool maxPower = false;
     for (int i = 1; i < argc; i++) {
@@ -31,9 +36,14 @@ int main(int argc, char** argv)
         else if (a == "--variant") variant = atoi(next());
         else if (a == "--maxpower") maxPower = true;
         else if (a == "--out") out = next();
+        else if (a == "--export") exportBase = next();
+        else if (a == "--checkpoint") checkpoint = next();
+        else if (a == "--resume") resume = next();
+        else if (a == "--device-bvh") deviceBvh = true;
         else { usage(); return a == "--help" ? 0 : 2; }
     }
     Mesh mesh;
+    mesh.buildBvhOnLoad = !deviceBvh;
     strncpy(mesh.modelFile, room.c_str(), 31);
     mesh.LoadMesh();
     if (!mesh.loadedMesh) { fprintf(stderr, "cannot load room: %s\n", mesh.lastError.c_str()); return 1; }
@@ -50,6 +60,7 @@ int main(int argc, char** argv)
     if (maxPower) rayTracer.viewMode = maxpower;
 
     rayTracer.ResetDosageMap();
+    if (!resume.empty() && !rayTracer.LoadCheckpoint(resume.c_str())) { fprintf(stderr, "%s\n", rayTracer.lastError.c_str()); return 1; }
     while (rayTracer.ok) {
         rayTracer.finishedComputation = rayTracer.currIterations >= rayTracer.maxIterations;
         if (rayTracer.finishedComputation) break;
@@ -63,6 +74,7 @@ int main(int argc, char** argv)
         rayTracer.compTime += time;
         std::cout << "Progress: " << rayTracer.progress << "% photon count: " << rayTracer.photonMapSize
                   << " delta time: " << time * 1000.0f << " total time: " << rayTracer.compTime * 1000.0f << std::endl;
+        if (!checkpoint.empty() && !rayTracer.SaveCheckpoint(checkpoint.c_str())) break;
         rayTracer.timerClock.reset();
     }
     if (!rayTracer.ok) { fprintf(stderr, "%s\n", rayTracer.lastError.c_str()); return 1; }
@@ -73,6 +85,7 @@ int main(int argc, char** argv)
     printf("triangles %d  rays %lld  mean %s %.6g  max %.6g  (%.1f Mrays/s wall)\n", mesh.triangleCount,
            (long long)rayTracer.RaysTraced(), maxPower ? "irradiance" : "dose", sum / mesh.triangleCount, mx,
            rayTracer.RaysTraced() / (rayTracer.compTime * 1e6));
+    if (!exportBase.empty() && !rayTracer.SaveDosageMap(exportBase.c_str())) { fprintf(stderr, "%s\n", rayTracer.lastError.c_str()); return 1; }
     if (!out.empty()) {
         std::ofstream f(out, std::ios::binary);
         f.write((const char*)dose, sizeof(float) * (size_t)mesh.triangleCount);

@@ -286,6 +286,27 @@ int uvrt_sim_reduce(uvrt_sim* s)
     return rt_status(s);
 }
 
+int uvrt_sim_save_dosage_map(uvrt_sim* s, const char* basePath)
+{
+    if (!s || !s->rt.ctx || !basePath) return UVRT_ERR_INVALID;
+    if (!s->rt.SaveDosageMap(basePath)) return s->rt.ok ? sim_fail(s, UVRT_ERR_IO, s->rt.lastError) : rt_status(s);
+    return UVRT_OK;
+}
+
+int uvrt_sim_save_checkpoint(uvrt_sim* s, const char* path)
+{
+    if (!s || !s->rt.ctx || !path) return UVRT_ERR_INVALID;
+    if (!s->rt.SaveCheckpoint(path)) return s->rt.ok ? sim_fail(s, UVRT_ERR_IO, s->rt.lastError) : rt_status(s);
+    return UVRT_OK;
+}
+
+int uvrt_sim_load_checkpoint(uvrt_sim* s, const char* path)
+{
+    if (!s || !s->rt.ctx || !path) return UVRT_ERR_INVALID;
+    if (!s->rt.LoadCheckpoint(path)) return s->rt.ok ? sim_fail(s, UVRT_ERR_IO, s->rt.lastError) : rt_status(s);
+    return UVRT_OK;
+}
+
 uvrt_ctx* uvrt_sim_ctx(uvrt_sim* s) { return s ? s->rt.ctx : nullptr; }
 
 int64_t uvrt_sim_rays_traced(const uvrt_sim* s) { return s ? s->rt.RaysTraced() : 0; }

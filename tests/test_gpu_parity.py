@@ -347,9 +347,11 @@ def test_shared_reciprocal_division_equals_ieee(ctx):
     assert bad1 == 0, "one-step Markstein quotient differs from __fdiv_rn"
 
 
-def test_error_codes_instead_of_aborts(uv, room):
+@pytest.mark.parametrize("host_repack", [0, 1])
+def test_error_codes_instead_of_aborts(uv, room, host_repack):
     tris, nodes, tri_idx, _ = room
     c = uv.Context(0)
+    c.set_option("host_repack", host_repack)
     with pytest.raises(uv.UvrtError) as e:
         c.extend(10)
     assert e.value.code == -3                                  # no scene yet
@@ -362,8 +364,15 @@ def test_error_codes_instead_of_aborts(uv, room):
         c.upload_scene(tris, nodes, bad_idx)
     loop = nodes.copy()
     loop[2]["leftFirst"] = 0                                    # a cycle
-    with pytest.raises(uv.UvrtError):
+    with pytest.raises(uv.UvrtError) as e:
         c.upload_scene(tris, loop, tri_idx)
+    assert e.value.code == -1 and "twice" in str(e.value)
+    span = nodes.copy()
+    leaf = int(np.flatnonzero(span["triCount"] > 0)[0])
+    span[leaf]["triCount"] = tris.shape[0] + 5                  # a leaf that runs off the end of triIdx
+    with pytest.raises(uv.UvrtError) as e:
+        c.upload_scene(tris, span, tri_idx)
+    assert e.value.code == -1 and "spans" in str(e.value)
     c.upload_scene(tris, nodes, tri_idx)                        # still usable
     c.generate((0, 0, 0), 1.0, 0, 0, 0)                         # zero rays: a no-op
     c.extend(0)
@@ -427,3 +436,107 @@ def test_raytracer_with_device_built_bvh(uv, room, golden):
     dose = sim.run()
     assert f"{T.fnv(dose):016x}" == golden["pass_lange_route"]["fnv_dose"]
     sim.close()
+
+
+def test_checkpoint_resume_is_bit_identical(uv, room, tmp_path):
+    """SURVEY section 5 (checkpoint/resume): photon and max maps + counters + the SEED chain make a run
+    resumable; two iterations in one go == one iteration, checkpoint, new RayTracer, one more."""
+    def new_sim():
+        s = uv.Sim(asset_root=T.DATA)
+        s.load_mesh("testroomopt")
+        s.init("lange_route")
+        s.set_params(maxIterations=2, photonCount=1 << 21)
+        return s
+    a = new_sim()
+    whole = a.run()
+    a.close()
+    b = new_sim()
+    b.reset_dosage_map()
+    assert b.tick() is False
+    ck = tmp_path / "run.ckpt"
+    b.save_checkpoint(ck)
+    b.close()
+    c = new_sim()
+    c.reset_dosage_map()
+    c.load_checkpoint(ck)
+    assert c.tick() is False
+    assert c.tick() is True                  # iteration 2 of 2 was the last one
+    resumed = c.read_dose()
+    assert resumed.tobytes() == whole.tobytes()
+    with pytest.raises(uv.UvrtError):
+        c.load_checkpoint(tmp_path / "missing.ckpt")
+    c.close()
+
+
+def test_export_dose_ply_json(uv, room, tmp_path):
+    """the dose map leaves the process as float32 + PLY with dosageToColor's colours."""
+    import json
+    s = uv.Sim(asset_root=T.DATA)
+    s.load_mesh("testroomopt")
+    s.init("route")
+    s.set_params(maxIterations=1, photonCount=1 << 20)
+    dose = s.run()
+    base = tmp_path / "room"
+    s.save_dosage_map(base)
+    color = s.ctx.read(uv.BUF.COLOR)
+    s.close()
+    n = room[0].shape[0]
+    assert np.fromfile(str(base) + ".dose.f32", dtype=np.float32).tobytes() == dose.tobytes()
+    meta = json.load(open(str(base) + ".json"))
+    assert meta["triangles"] == n and len(meta["route"]) == 12 and meta["view"] == "dose_mJ_cm2"
+    raw = open(str(base) + ".ply", "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    assert b"element vertex %d" % (3 * n) in head and b"element face %d" % n in head
+    vdt = np.dtype([("xyz", "<f4", 3), ("rgb", "u1", 3)])
+    v = np.frombuffer(body, dtype=vdt, count=3 * n)
+    tris = room[0].reshape(n, 4, 4)[:, :3, :3].reshape(3 * n, 3)
+    assert v["xyz"].tobytes() == np.ascontiguousarray(tris).tobytes()
+    want = (np.clip(color.reshape(3 * n, 3), 0, 1) * 255 + 0.5).astype(np.uint8)
+    assert np.array_equal(v["rgb"], want)
+    fdt = np.dtype([("k", "u1"), ("idx", "<i4", 3)])
+    f = np.frombuffer(body, dtype=fdt, offset=3 * n * vdt.itemsize, count=n)
+    assert (f["k"] == 3).all() and np.array_equal(f["idx"].ravel(), np.arange(3 * n))
+
+
+def test_device_scene_repack_equals_host_repack(uv, room):
+    """uvrt_upload_scene repacks the reference's arrays on the device (csrc/uvrt_scene_prep.cuh); the
+    host-side repack stays selectable ("host_repack").  Both must leave the same bytes in HBM: pairs
+    in pre-order, triangles in leaf order, same counts, depth and tame flag."""
+    from importlib import import_module
+    import sys as _sys
+    B = import_module("small-project-uv-robot-ray-tracer_b200.binding")
+    _sys.path.insert(0, T.ROOT + "/tools")
+    from soup import make_soup
+    rng = np.random.default_rng(3)
+    scenes = [(room[0], room[1], room[2])]
+    for n in (1, 2, 3, 17, 257, 5000):
+        m = np.zeros((n, 16), dtype=np.float32)
+        c = rng.uniform(-5, 5, (n, 3))
+        for k in range(3):
+            m[:, 4 * k: 4 * k + 3] = (c + rng.uniform(-0.2, 0.2, (n, 3))).astype(np.float32)
+        if n >= 17:
+            m[9:13] = m[8]                                      # a five-triangle leaf
+        scenes.append(B.build_bvh(m))
+    scenes.append(B.build_bvh(make_soup(200_000)))
+    wild = room[0].copy()
+    wild[:, 0:3] *= np.float32(3e6)                              # coordinates outside the tame range
+    scenes.append(B.build_bvh(wild))
+    images = []
+    for mode in (1, 0):
+        c = uv.Context(0)
+        c.set_option("host_repack", mode)
+        out = []
+        for tris, nodes, tri_idx in scenes:
+            c.upload_scene(tris, nodes, tri_idx)
+            info = c.scene_info()
+            out.append((info, c.get_option("scene_tame"), c.read(uv.BUF.PAIRS).tobytes(), c.read(uv.BUF.WTRIS).tobytes(),
+                        c.scene_upload_bytes()))
+        images.append(out)
+        c.close()
+    for k, (h, d) in enumerate(zip(*images)):
+        assert h[0] == d[0], f"scene {k}: scene_info differs: {h[0]} vs {d[0]}"
+        assert h[1] == d[1], f"scene {k}: tame flag differs"
+        assert h[2] == d[2], f"scene {k}: pairs differ"
+        assert h[3] == d[3], f"scene {k}: leaf triangles differ"
+        assert d[4] < h[4]                                       # raw arrays are smaller than the repacked image
+    assert images[0][-1][1] == 0 and images[0][0][1] == 1
