@@ -81,6 +81,9 @@ int uvrt_sim_read_dose(uvrt_sim* sim, float* dst, int capacity);
 /* Work sharing over ranks (launch k goes to rank k % count) and the final cross-rank reduction. */
 int uvrt_sim_set_shard(uvrt_sim* sim, int rank, int count);
 int uvrt_sim_reduce(uvrt_sim* sim);
+/* The rank that traces launch `launch` (counted over the whole run) of a route with `positions` lamp
+ * positions on `ranks` GPUs (RayTracer::ShardOwner). */
+int uvrt_host_shard_owner(long long launch, int positions, int ranks);
 /* Result export: <basePath>.dose.f32 (float32 per triangle), .ply (per-vertex colours of dosageToColor),
  * .json (parameters).  Call after uvrt_sim_shade / uvrt_sim_run. */
 int uvrt_sim_save_dosage_map(uvrt_sim* sim, const char* basePath);

@@ -160,6 +160,7 @@ def host():
         "uvrt_sim_save_checkpoint": (i, [vp, C.c_char_p]),
         "uvrt_sim_load_checkpoint": (i, [vp, C.c_char_p]),
         "uvrt_sim_set_shard": (i, [vp, i, i]),
+        "uvrt_host_shard_owner": (i, [C.c_longlong, i, i]),
         "uvrt_sim_reduce": (i, [vp]),
         "uvrt_sim_ctx": (vp, [vp]),
         "uvrt_sim_rays_traced": (C.c_int64, [vp]),

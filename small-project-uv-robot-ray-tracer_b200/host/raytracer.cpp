@@ -110,6 +110,22 @@ void RayTracer::ComputeDosageMap()
     }
 }
 
+// Which rank traces launch k of a run over a route of L positions.  Plain round-robin (k mod N) would
+// hand a rank the same few positions in every pass whenever gcd(L, N) > 1 (L = 12, N = 8: three
+// positions per rank), and positions differ in cost by up to 1.5x (24.9 - 36.6 node visits per ray on
+// lange_route), so the slowest rank would set the pace.  The deal is therefore rotated by s ranks per
+// pass, with the smallest s that makes L + s coprime to N: every position then visits every rank.
+int RayTracer::ShardOwner(long long launch, int L, int N)
+{
+    if (N <= 1) return 0;
+    if (L < 1) L = 1;
+    auto gcd = [](long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; };
+    int s = 0;
+    while (gcd((long long)L + s, N) != 1) s++;
+    const long long pass = launch / L;
+    return (int)((launch + (long long)s * pass) % N);
+}
+
 uint32_t RayTracer::SeedAfter(const float3& lp)
 {
     if (seedQueueHead < seedQueue.size()) {
@@ -131,7 +147,7 @@ void RayTracer::ComputeSingleLightDosageMap(LightPos lightPos, int photonsPerLig
 {
     if (!ok) return;
     float3 lightposition = make_float3(lightPos.position.x, mesh->floorHeight + lightHeight, lightPos.position.y);
-    const bool mine = shardCount <= 1 || (launchCounter % shardCount) == shardRank;
+    const bool mine = shardCount <= 1 || ShardOwner(launchCounter, (int)lightPositions.size(), shardCount) == shardRank;
     if (mine) {
         if (!Check(uvrt_trace(ctx, lightposition.x, lightposition.y, lightposition.z, lightLength, lightPos.duration, 0,
                               photonsPerLight, seedState),

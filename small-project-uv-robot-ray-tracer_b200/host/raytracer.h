@@ -69,8 +69,10 @@ public:
     // Device-side SEED of generate.cl:6 as seen by the next launch: starts at 0
     // and, like the reference's program-scope variable, survives ResetDosageMap().
     uint32_t seedState = 0;
-    // Work sharing between GPUs: launch k (counted over the whole run) is traced by the rank with
-    // k % shardCount == shardRank; every rank advances seedState and photonMapSize for every launch.
+    // Work sharing between GPUs: launch k (counted over the whole run) is traced by the rank
+    // ShardOwner(k, positions, shardCount) -- round-robin, rotated once per pass so that every rank sees
+    // every position; every rank advances seedState and photonMapSize for every launch.
+    static int ShardOwner(long long launch, int positions, int ranks);
     int shardRank = 0, shardCount = 1;
     long long launchCounter = 0;
     long long photonMapSizeTotal = 0;   // photonMapSize without the int overflow (see ComputeSingleLightDosageMap)

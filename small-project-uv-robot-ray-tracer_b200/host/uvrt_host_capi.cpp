@@ -307,6 +307,8 @@ int uvrt_sim_load_checkpoint(uvrt_sim* s, const char* path)
     return UVRT_OK;
 }
 
+int uvrt_host_shard_owner(long long launch, int positions, int ranks) { return RayTracer::ShardOwner(launch, positions, ranks); }
+
 uvrt_ctx* uvrt_sim_ctx(uvrt_sim* s) { return s ? s->rt.ctx : nullptr; }
 
 int64_t uvrt_sim_rays_traced(const uvrt_sim* s) { return s ? s->rt.RaysTraced() : 0; }

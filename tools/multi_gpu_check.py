@@ -3,7 +3,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29533 tools/multi_gpu_check.py
 
-Every rank traces its share of the launches (launch k -> rank k mod N, RayTracer::shardRank),
+Every rank traces its share of the launches (launches dealt by RayTracer::ShardOwner),
 the per-GPU maps are combined by uvrt_reduce (one NCCL all-reduce: sum of the photon map, max of
 the max map), and the result must equal -- bit for bit -- what rank 0 gets by running all launches
 alone, and the oracle's dose."""
