@@ -160,6 +160,8 @@ struct uvrt_ctx {
     int stageTiming = 0;
     int histMode = 0;
     int blocksPerSm = 0;      // 0: default for the variant
+    int genericOctant = 0;    // experiment: the one-thread-per-ray kernel without octant specialisation
+    int chunk = 128;          // rays per warp of the chunk-persistent kernel
     int simpleCfg = 1;        // 128 threads, <= 40 registers (48 resident warps per SM): fastest in the sweep
     int refill = 24;          // persistent kernels: refill when fewer lanes than this are busy
 
@@ -301,7 +303,25 @@ template <int DIV, int THREADS, int MINB>
 void launch_simple_cfg(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
     k_extend_simple<DIV, kStack, THREADS, MINB><<<grid_for(nRays, THREADS), THREADS, 0, ctx->stream>>>(
-        ctx->dCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm);
+        ctx->dCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm, 0, ctx->genericOctant);
+}
+
+template <int K, int CH>
+void launch_chunk_kc(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
+{
+    constexpr int THREADS = 128;
+    const long long warps = (nRays + CH - 1) / CH;
+    k_extend_chunk<DIV_MARKSTEIN1, kStack, K, CH, THREADS, 10><<<grid_for(warps * 32, THREADS), THREADS, 0, ctx->stream>>>(
+        ctx->dCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, (uint32_t)nRays, ctx->sceneTame, perm, ctx->refill);
+}
+
+template <int K>
+void launch_chunk_k(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
+{
+    if (ctx->chunk <= 64) launch_chunk_kc<K, 64>(ctx, nRays, perm);
+    else if (ctx->chunk <= 128) launch_chunk_kc<K, 128>(ctx, nRays, perm);
+    else if (ctx->chunk <= 256) launch_chunk_kc<K, 256>(ctx, nRays, perm);
+    else launch_chunk_kc<K, 1024>(ctx, nRays, perm);
 }
 
 template <int DIV>
@@ -433,6 +453,15 @@ int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     else if (v == 2 && ctx->fetchMode == 1 && ctx->pairsTex) launch_simple_tex<1>(ctx, nRays, perm);
     else if (v == 2 && ctx->fetchMode == 2 && ctx->pairsTex) launch_simple_tex<2>(ctx, nRays, perm);
     else if (v == 2) launch_simple<DIV_MARKSTEIN1>(ctx, nRays, perm);
+    else if (v >= 40 && v < 44) {
+        // chunk-persistent warps (k_extend_chunk): K = {1, 2, 4, 8}[v - 40]; "refill", "chunk" options
+        switch (v - 40) {
+        case 0: launch_chunk_k<1>(ctx, nRays, perm); break;
+        case 1: launch_chunk_k<2>(ctx, nRays, perm); break;
+        case 2: launch_chunk_k<4>(ctx, nRays, perm); break;
+        default: launch_chunk_k<8>(ctx, nRays, perm); break;
+        }
+    }
     else if (v >= 10 && v < 25) {
         int k = (v - 10) / 3, d = (v - 10) % 3;
         switch (k) {
@@ -1318,6 +1347,8 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
     else if (!strcmp(key, "blocks_per_sm")) ctx->blocksPerSm = value;
     else if (!strcmp(key, "refill")) ctx->refill = value;
     else if (!strcmp(key, "simple_cfg")) ctx->simpleCfg = value;
+    else if (!strcmp(key, "generic_octant")) ctx->genericOctant = value;
+    else if (!strcmp(key, "chunk")) ctx->chunk = value;
     else if (!strcmp(key, "pipeline")) ctx->pipeline = value;
     else if (!strcmp(key, "host_repack")) ctx->hostRepack = value;
     else if (!strcmp(key, "fetch_mode")) ctx->fetchMode = value;
@@ -1348,6 +1379,8 @@ int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value)
     else if (!strcmp(key, "scene_tame")) *value = ctx->sceneTame;
     else if (!strcmp(key, "refill")) *value = ctx->refill;
     else if (!strcmp(key, "simple_cfg")) *value = ctx->simpleCfg;
+    else if (!strcmp(key, "generic_octant")) *value = ctx->genericOctant;
+    else if (!strcmp(key, "chunk")) *value = ctx->chunk;
     else if (!strcmp(key, "pipeline")) *value = ctx->pipeline;
     else if (!strcmp(key, "host_repack")) *value = ctx->hostRepack;
     else if (!strcmp(key, "fetch_mode")) *value = ctx->fetchMode;

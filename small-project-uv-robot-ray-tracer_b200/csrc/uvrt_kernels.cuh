@@ -532,14 +532,15 @@ template <int DIV, int STACK, int THREADS, int MINBLOCKS, int FETCH = 0>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_extend_simple(int* __restrict__ counts, const float4* __restrict__ wtris,
                                                        float4* __restrict__ rays, const float4* __restrict__ pairs,
                                                        uint32_t rootRef, long long nRays, int sceneTame,
-                                                       const uint32_t* __restrict__ perm, cudaTextureObject_t tex = 0)
+                                                       const uint32_t* __restrict__ perm, cudaTextureObject_t tex = 0,
+                                                       int genericOctant = 0)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nRays) return;
     if (perm) i = perm[i];
     RayCtx ray;
     load_ray(rays, i, ray);
-    trace_one<DIV, STACK, FETCH>(ray, pairs, wtris, rootRef, sceneTame != 0, perm != nullptr, tex);
+    trace_one<DIV, STACK, FETCH>(ray, pairs, wtris, rootRef, sceneTame != 0, perm != nullptr && !genericOctant, tex);
     store_hit(rays, i, ray);
     if (ray.dist != kNoHit) atomicAdd(&counts[ray.tri], 1);
 }
@@ -671,6 +672,103 @@ k_extend_persist(int* __restrict__ counts, const float4* __restrict__ wtris, flo
         for (int i = threadIdx.x; i < (1 << HBITS); i += THREADS) {
             int c = tab.cnt[i];
             if (c) atomicAdd(&counts[tab.tag[i]], c);
+        }
+    }
+}
+
+
+// Variant C: persistent warps over PRIVATE chunks of the (binned) ray order.  Warp w owns rays
+// [w*CH, (w+1)*CH) of the permutation; lanes whose ray has finished are refilled from the warp's own
+// chunk (a warp-uniform cursor, no atomics) once fewer than `refill` lanes are busy.  Unlike variant B's
+// global queue this keeps the rays of a warp neighbours in the binned order, so the coherence the
+// binning created survives the refill; the tail where a warp waits for its longest ray is paid once per
+// CH rays instead of once per 32.  Per-ray test sequence as in variant A.
+template <int DIV, int STACK, int K, int CH, int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS)
+k_extend_chunk(int* __restrict__ counts, const float4* __restrict__ wtris, float4* __restrict__ rays,
+               const float4* __restrict__ pairs, uint32_t rootRef, uint32_t nRays, int sceneTame,
+               const uint32_t* __restrict__ perm, int refill)
+{
+    uint32_t stack[STACK];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * THREADS + threadIdx.x) >> 5;
+    uint32_t next = warp * (uint32_t)CH;
+    const uint32_t end = min(next + (uint32_t)CH, nRays);
+    if (next >= nRays) return;
+    RayCtx ray;
+    ray.ox = ray.oy = ray.oz = ray.dx = ray.dy = ray.dz = 0.0f;
+    ray.noXY = ray.noZZ = ray.rXY = ray.rZZ = ray.ndXY = ray.ndZZ = 0ull;
+    ray.dist = kNoHit; ray.tri = 0;
+    uint32_t cur = 0, rayIdx = 0xffffffffu;
+    int sp = 0;
+    bool busy = false, tame = false;
+
+    for (;;) {
+        // ---- refill from the warp's own chunk (warp-converged) ----
+        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+        if (idle && next < end) {
+            if (!busy) {
+                const uint32_t idx = next + __popc(idle & ((1u << lane) - 1u));
+                if (idx < end) {
+                    rayIdx = perm ? perm[idx] : idx;
+                    load_ray(rays, rayIdx, ray);
+                    tame = false;
+                    if (DIV != DIV_IEEE && sceneTame && ray_is_tame(ray)) {
+                        tame = true;
+                        make_tame(ray);
+                    }
+                    cur = rootRef; sp = 0; busy = true;
+                }
+            }
+            next = min(next + (uint32_t)__popc(idle), end);
+        }
+        unsigned act = __ballot_sync(0xffffffffu, busy);
+        if (act == 0u) break;
+
+        // ---- traverse until too few lanes are busy ----
+        for (;;) {
+#pragma unroll 1
+            for (int k = 0; k < K && busy && !(cur & kLeafFlag); k++) {
+                const float4* p = pairs + 4ull * cur;
+                W4 ca = ldg256w(p), cb = ldg256w(p + 2);
+                float t1, t2;
+                bool h1, h2;
+                if (DIV == DIV_IEEE || !tame) {
+                    h1 = intersect_aabb<DIV_IEEE, -1>(ray, ca, t1);
+                    h2 = intersect_aabb<DIV_IEEE, -1>(ray, cb, t2);
+                } else {
+                    h1 = intersect_aabb<DIV, -1>(ray, ca, t1);
+                    h2 = intersect_aabb<DIV, -1>(ray, cb, t2);
+                }
+                uint32_t first, second;
+                bool pushSecond;
+                if (order_children(h1, h2, t1, t2, child_ref(ca), child_ref(cb), first, second, pushSecond)) {
+                    cur = first;
+                    if (pushSecond) stack[sp++] = second;
+                } else {
+                    if (sp == 0) busy = false; else cur = stack[--sp];
+                }
+            }
+            if (busy && (cur & kLeafFlag)) {
+                uint32_t slot = cur & ~kLeafFlag;
+                uint32_t w;
+                do {
+                    const float4* t = wtris + 4ull * slot;
+                    F8 ta = ldg256(t), tb = ldg256(t + 2);
+                    w = __float_as_uint(ta.lo.w);
+                    intersect_tri(ray, ta.lo, ta.hi, tb.lo);
+                    slot++;
+                } while (!(w & kLastFlag));
+                if (sp == 0) busy = false; else cur = stack[--sp];
+            }
+            if (!busy && rayIdx != 0xffffffffu) {
+                store_hit(rays, rayIdx, ray);
+                if (ray.dist != kNoHit) atomicAdd(&counts[ray.tri], 1);
+                rayIdx = 0xffffffffu;
+            }
+            act = __ballot_sync(0xffffffffu, busy);
+            if (act == 0u) break;
+            if (next < end && (int)__popc(act) < refill) break;
         }
     }
 }

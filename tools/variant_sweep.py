@@ -74,6 +74,8 @@ def main():
     ap.add_argument("--variants", default="0,1,2")
     ap.add_argument("--hist", default="0", help="hist_mode values (persistent variants only)")
     ap.add_argument("--refill", default="24", help="refill thresholds (persistent variants only)")
+    ap.add_argument("--chunk", default="128", help="rays per warp (chunk-persistent variants 40-43 only)")
+    ap.add_argument("--generic", default="0", help="generic_octant values (one-thread-per-ray variants only)")
     ap.add_argument("--cfg", default="1", help="simple_cfg values (one-thread-per-ray variants only)")
     ap.add_argument("--fetch", default="0", help="fetch_mode values: 0 LSU, 1 texture, 2 mixed (variant 2 only)")
     ap.add_argument("--bin", default="16,32,128", help="device binning: 0 (off) or nY,nT,nP; ';'-separated")
@@ -104,11 +106,15 @@ def main():
                 c.set_option("bin_t", bt)
                 c.set_option("bin_p", bp)
             persistent = v >= 10
-            knobs = itertools.product(ints(args.hist) if persistent else [0],
+            knobs = itertools.product(ints(args.hist) if persistent and v < 40 else [0],
                                       ints(args.refill) if persistent else [24],
                                       [1] if persistent else ints(args.cfg),
-                                      ints(args.fetch) if v == 2 else [0])
-            for hist, refill, cfg, fetch in knobs:
+                                      ints(args.fetch) if v == 2 else [0],
+                                      ints(args.chunk) if v >= 40 else [128],
+                                      [0] if persistent else ints(args.generic))
+            for hist, refill, cfg, fetch, chunk, generic in knobs:
+                c.set_option("chunk", chunk)
+                c.set_option("generic_octant", generic)
                 c.set_option("extend_variant", v)
                 c.set_option("hist_mode", hist)
                 c.set_option("refill", refill)
@@ -132,10 +138,10 @@ def main():
                     ref_counts = counts
                 best = min(times)
                 print(json.dumps({"pos": pi, "sort": sort, "bin": binspec, "variant": v, "hist": hist, "refill": refill,
-                                  "cfg": cfg, "fetch": fetch, "ms_best": round(best, 4),
+                                  "cfg": cfg, "fetch": fetch, "chunk": chunk, "generic": generic, "ms_best": round(best, 4),
                                   "ms_med": round(float(np.median(times)), 4), "mrays_s": round(P / best / 1e3, 1),
                                   "counts_equal": bool(np.array_equal(counts, ref_counts))}), flush=True)
-    for k, v in (("extend_variant", -1), ("bin_rays", 1), ("hist_mode", 0), ("fetch_mode", 0), ("simple_cfg", 1), ("refill", 24)):
+    for k, v in (("extend_variant", -1), ("bin_rays", 1), ("hist_mode", 0), ("fetch_mode", 0), ("simple_cfg", 1), ("refill", 24), ("chunk", 128), ("generic_octant", 0)):
         c.set_option(k, v)
 
 
