@@ -48,6 +48,9 @@ int uvrt_sim_load_mesh(uvrt_sim* sim, const char* modelFile);
 /* deviceBvh != 0: load_mesh / set_triangles skip the CPU BVH build and uvrt_sim_init builds the tree
  * on the device (uvrt_build_bvh); the result is the same tree. */
 int uvrt_sim_set_device_bvh(uvrt_sim* sim, int deviceBvh);
+/* wholeScene != 0: load_mesh reads every triangle primitive of the default scene's node tree with the node
+ * transforms applied; 0 (default) = the reference's loader: meshes[0].primitives[0] only (mesh.cpp:28). */
+int uvrt_sim_set_whole_scene(uvrt_sim* sim, int wholeScene);
 /* Mesh from caller-supplied triangles (n x 64 B, reference layout); builds the BVH.  CPU only. */
 int uvrt_sim_set_triangles(uvrt_sim* sim, const void* tris, int n);
 int uvrt_sim_mesh_info(const uvrt_sim* sim, int* triangleCount, float* floorHeight, unsigned* nodesUsed);

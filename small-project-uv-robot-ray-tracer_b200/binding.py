@@ -139,6 +139,7 @@ def host():
         "uvrt_sim_load_mesh": (i, [vp, C.c_char_p]),
         "uvrt_sim_set_triangles": (i, [vp, vp, i]),
         "uvrt_sim_set_device_bvh": (i, [vp, i]),
+        "uvrt_sim_set_whole_scene": (i, [vp, i]),
         "uvrt_sim_mesh_info": (i, [vp, C.POINTER(i), C.POINTER(f), C.POINTER(C.c_uint)]),
         "uvrt_sim_mesh_data": (i, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "uvrt_sim_load_route": (i, [vp, C.c_char_p]),
@@ -383,6 +384,9 @@ class Sim:
 
     def load_mesh(self, model_file):
         self.check(self.H.uvrt_sim_load_mesh(self.h, model_file.encode()))
+
+    def set_whole_scene(self, on=True):
+        self.check(self.H.uvrt_sim_set_whole_scene(self.h, int(on)))
 
     def set_device_bvh(self, on=True):
         self.check(self.H.uvrt_sim_set_device_bvh(self.h, int(on)))

@@ -1,7 +1,8 @@
 // mesh.cpp -- binary glTF (.glb) room loader and floor-height estimate.
 // Behaviour follows /root/reference/mesh.cpp:5-136: only meshes[0].primitives[0] is read,
 // POSITION (float VEC3) is de-indexed through u16 or u32 indices into 64-byte Tri records,
-// then the floor height is estimated and the BVH built.  The container is parsed directly
+// then the floor height is estimated and the BVH built.  Opt-in (Mesh::loadWholeScene):
+// every triangle primitive of the default scene's node tree, node transforms applied.  The container is parsed directly
 // (12-byte header, JSON chunk, BIN chunk) instead of through tinygltf.
 #include "precomp.h"
 #include "json_min.h"
@@ -105,47 +106,160 @@ void Mesh::LoadMesh()
     if (binHdr + 8 + binLen > total) return bail("truncated BIN chunk");
     const unsigned char* bin = (const unsigned char*)&file[binHdr + 8];
 
-    const uvrt_json::Value& prim = js["meshes"][0]["primitives"][0];
-    if (prim.kind != uvrt_json::Value::Object) return bail("meshes[0].primitives[0] missing");
-    if (!prim["attributes"]["POSITION"].is_number() || !prim["indices"].is_number()) return bail("primitive needs POSITION and indices");
-    AccessorView pos, idx, uv;
-    std::string err;
-    if (!resolve(js, bin, binLen, prim["attributes"]["POSITION"].as_int(), 12, pos, err)) return bail("POSITION: " + err);
-    if (pos.componentType != 5126) return bail("POSITION must be float");
-    long long idxAcc = prim["indices"].as_int();
-    int idxType = (int)js["accessors"][(size_t)idxAcc]["componentType"].as_int(0);
-    if (idxType != 5123 && idxType != 5125) return bail("indices must be u16 or u32");   // mesh.cpp:44-51
-    size_t idxBytes = idxType == 5123 ? 2 : 4;
-    if (!resolve(js, bin, binLen, idxAcc, idxBytes, idx, err)) return bail("indices: " + err);
-    bool haveUv = prim["attributes"]["TEXCOORD_0"].is_number() &&
-                  resolve(js, bin, binLen, prim["attributes"]["TEXCOORD_0"].as_int(), 8, uv, err) && uv.componentType == 5126;
+    // de-indexed positions (9 floats per triangle) and uvs (6 per triangle) of everything that is loaded
+    std::vector<float> outPos, outUv;
+    std::string perr;
+    // one primitive; `xf` (column-major 4x4, double) is applied to the positions when non-null
+    auto add_primitive = [&](const uvrt_json::Value& prim, const double* xf, bool strict) -> bool {
+        if (prim.kind != uvrt_json::Value::Object) { perr = "primitive missing"; return false; }
+        const long long mode = prim["mode"].is_number() ? prim["mode"].as_int() : 4;
+        if (!strict && mode != 4) return true;                       // points, lines, strips: not surfaces
+        if (!prim["attributes"]["POSITION"].is_number()) { perr = "primitive needs POSITION"; return false; }
+        if (strict && !prim["indices"].is_number()) { perr = "primitive needs POSITION and indices"; return false; }
+        AccessorView pos, idx, uv;
+        std::string err;
+        if (!resolve(js, bin, binLen, prim["attributes"]["POSITION"].as_int(), 12, pos, err)) { perr = "POSITION: " + err; return false; }
+        if (pos.componentType != 5126) { perr = "POSITION must be float"; return false; }
+        const bool indexed = prim["indices"].is_number();
+        size_t idxBytes = 0;
+        if (indexed) {
+            long long idxAcc = prim["indices"].as_int();
+            int idxType = (int)js["accessors"][(size_t)idxAcc]["componentType"].as_int(0);
+            // the reference reads u16 and u32 (mesh.cpp:44-51); u8 is the third type glTF allows
+            if (idxType == 5123) idxBytes = 2;
+            else if (idxType == 5125) idxBytes = 4;
+            else if (idxType == 5121 && !strict) idxBytes = 1;
+            else { perr = "indices must be u16 or u32"; return false; }
+            if (!resolve(js, bin, binLen, idxAcc, idxBytes, idx, err)) { perr = "indices: " + err; return false; }
+        }
+        bool haveUv = prim["attributes"]["TEXCOORD_0"].is_number() &&
+                      resolve(js, bin, binLen, prim["attributes"]["TEXCOORD_0"].as_int(), 8, uv, err) && uv.componentType == 5126;
+        const size_t nCorners = indexed ? idx.count : pos.count;
+        const size_t nTri = nCorners / 3;
+        auto index_at = [&](size_t k) -> size_t {
+            if (!indexed) return k;
+            const unsigned char* p = idx.data + k * idx.stride;
+            if (idxBytes == 1) return *p;
+            if (idxBytes == 2) { uint16_t v; memcpy(&v, p, 2); return v; }
+            uint32_t v; memcpy(&v, p, 4); return v;
+        };
+        const size_t base = outPos.size() / 9;
+        outPos.resize((base + nTri) * 9);
+        outUv.resize((base + nTri) * 6, 0.0f);
+        for (size_t t = 0; t < nTri; t++) {
+            for (int c = 0; c < 3; c++) {
+                size_t v = index_at(t * 3 + c);
+                if (v >= pos.count) { perr = "vertex index out of range"; return false; }
+                float p[3];
+                memcpy(p, pos.data + v * pos.stride, 12);
+                if (xf) {
+                    const double x = p[0], y = p[1], z = p[2];
+                    p[0] = (float)(xf[0] * x + xf[4] * y + xf[8] * z + xf[12]);
+                    p[1] = (float)(xf[1] * x + xf[5] * y + xf[9] * z + xf[13]);
+                    p[2] = (float)(xf[2] * x + xf[6] * y + xf[10] * z + xf[14]);
+                }
+                memcpy(&outPos[(base + t) * 9 + c * 3], p, 12);
+                if (haveUv && v < uv.count) memcpy(&outUv[(base + t) * 6 + c * 2], uv.data + v * uv.stride, 8);
+            }
+        }
+        return true;
+    };
 
-    const size_t nTri = idx.count / 3;
+    if (!loadWholeScene) {
+        // the reference: meshes[0].primitives[0] only, node transforms ignored (mesh.cpp:28)
+        const uvrt_json::Value& prim = js["meshes"][0]["primitives"][0];
+        if (prim.kind != uvrt_json::Value::Object) return bail("meshes[0].primitives[0] missing");
+        if (!add_primitive(prim, nullptr, true)) return bail(perr);
+    } else {
+        // every triangle primitive of every mesh instanced by the default scene's node tree, with the
+        // nodes' transforms (matrix or translation * rotation * scale) applied
+        struct Frame { size_t node; double m[16]; int depth; };
+        auto mul = [](const double* a, const double* b, double* o) {
+            for (int c = 0; c < 4; c++)
+                for (int r = 0; r < 4; r++) {
+                    double v = 0;
+                    for (int k = 0; k < 4; k++) v += a[k * 4 + r] * b[c * 4 + k];
+                    o[c * 4 + r] = v;
+                }
+        };
+        auto local = [](const uvrt_json::Value& n, double* m) {
+            for (int i = 0; i < 16; i++) m[i] = (i % 5 == 0) ? 1.0 : 0.0;
+            if (n["matrix"].size() == 16) {
+                for (int i = 0; i < 16; i++) m[i] = n["matrix"][(size_t)i].num;
+                return;
+            }
+            double t[3] = {0, 0, 0}, q[4] = {0, 0, 0, 1}, sc[3] = {1, 1, 1};
+            if (n["translation"].size() == 3) for (int i = 0; i < 3; i++) t[i] = n["translation"][(size_t)i].num;
+            if (n["rotation"].size() == 4) for (int i = 0; i < 4; i++) q[i] = n["rotation"][(size_t)i].num;
+            if (n["scale"].size() == 3) for (int i = 0; i < 3; i++) sc[i] = n["scale"][(size_t)i].num;
+            const double x = q[0], y = q[1], z = q[2], w = q[3];
+            const double r[9] = {1 - 2 * (y * y + z * z), 2 * (x * y + z * w), 2 * (x * z - y * w),      // column 0
+                                 2 * (x * y - z * w), 1 - 2 * (x * x + z * z), 2 * (y * z + x * w),      // column 1
+                                 2 * (x * z + y * w), 2 * (y * z - x * w), 1 - 2 * (x * x + y * y)};     // column 2
+            for (int c = 0; c < 3; c++)
+                for (int k = 0; k < 3; k++) m[c * 4 + k] = r[c * 3 + k] * sc[c];
+            m[12] = t[0]; m[13] = t[1]; m[14] = t[2];
+        };
+        const uvrt_json::Value& nodes = js["nodes"];
+        std::vector<Frame> stack;
+        const uvrt_json::Value& roots = js["scenes"][(size_t)js["scene"].as_int(0)]["nodes"];
+        double ident[16];
+        for (int i = 0; i < 16; i++) ident[i] = (i % 5 == 0) ? 1.0 : 0.0;
+        if (roots.size() == 0) {
+            // no scene graph: every mesh once, untransformed
+            for (size_t mi = 0; mi < js["meshes"].size(); mi++)
+                for (size_t pi = 0; pi < js["meshes"][mi]["primitives"].size(); pi++)
+                    if (!add_primitive(js["meshes"][mi]["primitives"][pi], nullptr, false)) return bail(perr);
+        }
+        for (size_t i = roots.size(); i-- > 0;) {
+            Frame f;
+            f.node = (size_t)roots[i].as_int(-1);
+            memcpy(f.m, ident, sizeof ident);
+            f.depth = 0;
+            stack.push_back(f);
+        }
+        size_t visited = 0;
+        while (!stack.empty()) {
+            Frame f = stack.back();
+            stack.pop_back();
+            const uvrt_json::Value& n = nodes[f.node];
+            if (n.kind != uvrt_json::Value::Object) return bail("scene references a missing node");
+            if (f.depth > 256 || ++visited > 16 * (nodes.size() + 1)) return bail("node hierarchy is cyclic");
+            double loc[16], world[16];
+            local(n, loc);
+            mul(f.m, loc, world);
+            if (n["mesh"].is_number()) {
+                const uvrt_json::Value& prims = js["meshes"][(size_t)n["mesh"].as_int()]["primitives"];
+                for (size_t pi = 0; pi < prims.size(); pi++)
+                    if (!add_primitive(prims[pi], world, false)) return bail(perr);
+            }
+            const uvrt_json::Value& kids = n["children"];
+            for (size_t i = kids.size(); i-- > 0;) {
+                Frame c;
+                c.node = (size_t)kids[i].as_int(-1);
+                memcpy(c.m, world, sizeof world);
+                c.depth = f.depth + 1;
+                stack.push_back(c);
+            }
+        }
+    }
+
+    const size_t nTri = outPos.size() / 9;
     if (nTri == 0) return bail("no triangles");
+    if (nTri > 0x3fffffffu) return bail("too many triangles");
     void* mem = nullptr;
     if (posix_memalign(&mem, 64, sizeof(Tri) * nTri) != 0) return bail("out of memory");
     memset(mem, 0, sizeof(Tri) * nTri);   // the reference leaves the pad lanes uninitialised
     triangles = (Tri*)mem;
     vertices = new float[nTri * 9];
     uvcoords = new float[nTri * 6]();
-    auto index_at = [&](size_t k) -> size_t {
-        const unsigned char* p = idx.data + k * idx.stride;
-        if (idxBytes == 2) { uint16_t v; memcpy(&v, p, 2); return v; }
-        uint32_t v; memcpy(&v, p, 4); return v;
-    };
+    memcpy(vertices, outPos.data(), sizeof(float) * nTri * 9);
+    memcpy(uvcoords, outUv.data(), sizeof(float) * nTri * 6);
     for (size_t t = 0; t < nTri; t++) {
-        float3_strict* dst[3] = {&triangles[t].vertex0, &triangles[t].vertex1, &triangles[t].vertex2};
-        for (int c = 0; c < 3; c++) {
-            size_t v = index_at(t * 3 + c);
-            if (v >= pos.count) { Release(); return bail("vertex index out of range"); }
-            float p[3];
-            memcpy(p, pos.data + v * pos.stride, 12);
-            *dst[c] = make_float3_strict(p[0], p[1], p[2]);
-            vertices[t * 9 + c * 3 + 0] = p[0];
-            vertices[t * 9 + c * 3 + 1] = p[1];
-            vertices[t * 9 + c * 3 + 2] = p[2];
-            if (haveUv && v < uv.count) memcpy(&uvcoords[t * 6 + c * 2], uv.data + v * uv.stride, 8);
-        }
+        const float* p = &vertices[t * 9];
+        triangles[t].vertex0 = make_float3_strict(p[0], p[1], p[2]);
+        triangles[t].vertex1 = make_float3_strict(p[3], p[4], p[5]);
+        triangles[t].vertex2 = make_float3_strict(p[6], p[7], p[8]);
     }
     vertexCount = (int)(nTri * 9);
     triangleCount = (int)nTri;

@@ -33,6 +33,10 @@ public:
     // false: LoadMesh / SetTriangles leave `bvh` empty and RayTracer::Init builds it on the device
     // (uvrt_build_bvh) -- the reference always builds on the CPU inside LoadMesh (mesh.cpp:96).
     bool buildBvhOnLoad = true;
+    // true: load every TRIANGLES primitive of every mesh the default scene instances, with the node
+    // transforms applied (u8/u16/u32 or no indices).  false (default) = the reference: only
+    // meshes[0].primitives[0], transforms ignored (mesh.cpp:28).
+    bool loadWholeScene = false;
 
     Tri* triangles = 0;
     int triangleCount = 0;

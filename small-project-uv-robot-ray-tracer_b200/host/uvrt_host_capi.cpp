@@ -63,6 +63,13 @@ int uvrt_sim_set_device_bvh(uvrt_sim* s, int deviceBvh)
     return UVRT_OK;
 }
 
+int uvrt_sim_set_whole_scene(uvrt_sim* s, int wholeScene)
+{
+    if (!s) return UVRT_ERR_INVALID;
+    s->mesh.loadWholeScene = wholeScene != 0;
+    return UVRT_OK;
+}
+
 int uvrt_sim_set_triangles(uvrt_sim* s, const void* tris, int n)
 {
     if (!s || !tris || n <= 0) return UVRT_ERR_INVALID;

@@ -236,3 +236,95 @@ def test_swap_partition_closed_form():
         p = rnd.random()
         left = [rnd.random() < p for _ in range(n)]
         assert loop(range(n), left) == closed_form(range(n), left)
+
+
+def _write_glb(path, js, blob):
+    import json as _json
+    import struct
+    j = _json.dumps(js).encode()
+    j += b" " * (-len(j) % 4)
+    blob += b"\0" * (-len(blob) % 4)
+    total = 12 + 8 + len(j) + 8 + len(blob)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4sII", b"glTF", 2, total))
+        f.write(struct.pack("<II", len(j), 0x4E4F534A) + j)
+        f.write(struct.pack("<II", len(blob), 0x004E4942) + blob)
+
+
+def test_whole_scene_loader_multi_primitive_and_transforms(uv, tmp_path):
+    """SURVEY 8(f)-4: Mesh::loadWholeScene reads every triangle primitive the default scene instances
+    (two meshes, u8 / u16 / no indices, a skipped LINES primitive) and applies the node transforms
+    (matrix, and translation * rotation * scale through a child node).  The default stays the reference's
+    meshes[0].primitives[0] with transforms ignored (mesh.cpp:28)."""
+    rng = np.random.default_rng(11)
+    p0 = rng.uniform(-1, 1, (6, 3)).astype("<f4")       # mesh 0 / primitive 0: u16 indices
+    i0 = np.array([0, 1, 2, 3, 4, 5, 0, 2, 4], dtype="<u2")
+    p1 = rng.uniform(-1, 1, (5, 3)).astype("<f4")       # mesh 0 / primitive 1: u8 indices
+    i1 = np.array([4, 3, 2, 1, 0, 2], dtype="u1")
+    p2 = rng.uniform(-1, 1, (6, 3)).astype("<f4")       # mesh 1 / primitive 0: not indexed
+    chunks, views, accs = [], [], []
+
+    def add(arr, ctype, typ):
+        off = sum(len(c) for c in chunks)
+        raw = arr.tobytes()
+        raw += b"\0" * (-len(raw) % 4)
+        chunks.append(raw)
+        views.append({"buffer": 0, "byteOffset": off, "byteLength": arr.nbytes})
+        accs.append({"bufferView": len(views) - 1, "componentType": ctype, "count": len(arr), "type": typ})
+        return len(accs) - 1
+    a_p0, a_i0 = add(p0, 5126, "VEC3"), add(i0, 5123, "SCALAR")
+    a_p1, a_i1 = add(p1, 5126, "VEC3"), add(i1, 5121, "SCALAR")
+    a_p2 = add(p2, 5126, "VEC3")
+    q = np.array([0.1, 0.7, -0.2, 0.6])
+    q /= np.linalg.norm(q)
+    matrix = [1, 0, 0, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0.5, -2, 3, 1]          # column-major
+    js = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0, 2]}],
+          "nodes": [{"mesh": 0, "translation": [1, 2, 3], "rotation": q.tolist(), "scale": [2, 0.5, 1.5], "children": [1]},
+                    {"mesh": 1, "translation": [0, -1, 0]},
+                    {"mesh": 1, "matrix": matrix}],
+          "meshes": [{"primitives": [{"attributes": {"POSITION": a_p0}, "indices": a_i0},
+                                     {"attributes": {"POSITION": a_p1}, "indices": a_i1, "mode": 4},
+                                     {"attributes": {"POSITION": a_p1}, "indices": a_i1, "mode": 1}]},
+                     {"primitives": [{"attributes": {"POSITION": a_p2}}]}],
+          "buffers": [{"byteLength": sum(len(c) for c in chunks)}], "bufferViews": views, "accessors": accs}
+    os.makedirs(tmp_path / "rooms")
+    _write_glb(tmp_path / "rooms" / "multi.glb", js, b"".join(chunks))
+
+    def trs(t, quat, s):
+        x, y, z, w = quat
+        r = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        m = np.eye(4)
+        m[:3, :3] = r * np.asarray(s)[None, :]
+        m[:3, 3] = t
+        return m
+    m0 = trs([1, 2, 3], q, [2, 0.5, 1.5])
+    m1 = m0 @ trs([0, -1, 0], [0, 0, 0, 1], [1, 1, 1])
+    m2 = np.array(matrix, dtype=np.float64).reshape(4, 4).T
+
+    def apply(m, pts):
+        return (pts.astype(np.float64) @ m[:3, :3].T + m[:3, 3]).astype(np.float32)
+    want = np.concatenate([apply(m0, p0[i0.astype(int)]), apply(m0, p1[i1.astype(int)]), apply(m1, p2), apply(m2, p2)]).reshape(-1, 9)
+
+    sim = uv.Sim(asset_root=str(tmp_path))
+    sim.set_whole_scene(True)
+    sim.load_mesh("multi")
+    tris = sim.mesh_data()[0]
+    got = np.concatenate([tris[:, 0:3], tris[:, 4:7], tris[:, 8:11]], axis=1)
+    assert got.shape == want.shape == (3 + 2 + 2 + 2, 9)
+    assert np.allclose(got, want, rtol=0, atol=2e-6), np.abs(got - want).max()
+    # default = the reference's loader: first primitive of the first mesh, as stored
+    sim.set_whole_scene(False)
+    sim.load_mesh("multi")
+    tris = sim.mesh_data()[0]
+    got = np.concatenate([tris[:, 0:3], tris[:, 4:7], tris[:, 8:11]], axis=1)
+    assert got.tobytes() == p0[i0.astype(int)].reshape(-1, 9).tobytes()
+    # the real room has one mesh under identity transforms: both modes give the same triangles
+    os.symlink(T.ROOM, tmp_path / "rooms" / "room.glb")
+    sim.load_mesh("room")
+    a = sim.mesh_data()[0].copy()
+    sim.set_whole_scene(True)
+    sim.load_mesh("room")
+    assert sim.mesh_data()[0].tobytes() == a.tobytes()
+    uv.Sim(asset_root=T.DATA)  # restore the asset root for later tests
