@@ -128,6 +128,18 @@ struct uvrt_ctx {
     RaySlot& rs() { return slots[slot]; }
     cudaStream_t genStream = nullptr;    // generate (+ bin count) of pipelined uvrt_trace calls
     int pipeline = 1;
+    // uvrt_trace with "overlap_extend": the extend kernels of consecutive launches run on two streams
+    // (slot 0 / slot 1) with a count buffer each, so the tail of extend k overlaps the head of extend
+    // k+1; the accumulates stay on the main stream, in launch order
+    int overlapExtend = 1;
+    cudaStream_t extStream[2] = {nullptr, nullptr};
+    cudaStream_t accStream = nullptr;    // accumulates of overlapped traces (high priority: tiny kernels, they gate the next extend)
+    cudaEvent_t extDone[2] = {nullptr, nullptr}, accDone[2] = {nullptr, nullptr}, forkEv = nullptr;
+    bool extUsed[2] = {false, false}, accUsed[2] = {false, false};
+    bool mainForeign = true;             // something other than an overlapped trace touched the main stream
+    int* dCountsAlt = nullptr;           // count buffer of slot 1
+    cudaStream_t xStream = nullptr;      // stream / count buffer of the extend being launched
+    int* xCounts = nullptr;
     long long lastRays = 0;
     unsigned int* dQueue = nullptr;      // persistent-kernel work counter
     uint32_t* dSeeds = nullptr;
@@ -204,7 +216,13 @@ int fail(uvrt_ctx* c, int code, const char* fmt, ...)
     } while (0)
 
 struct Bind {
-    explicit Bind(uvrt_ctx* c) { cudaGetDevice(&prev); if (prev != c->device) cudaSetDevice(c->device); dev = c->device; }
+    explicit Bind(uvrt_ctx* c)
+    {
+        cudaGetDevice(&prev);
+        if (prev != c->device) cudaSetDevice(c->device);
+        dev = c->device;
+        c->mainForeign = true;   // every entry point but the overlapped uvrt_trace clears nothing: see uvrt_trace
+    }
     ~Bind() { if (prev != dev && prev >= 0) cudaSetDevice(prev); }
     int prev = -1, dev = -1;
 };
@@ -302,8 +320,8 @@ constexpr int kDefaultVariant = 2;   // one thread per ray, one-step shared-reci
 template <int DIV, int THREADS, int MINB>
 void launch_simple_cfg(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
-    k_extend_simple<DIV, kStack, THREADS, MINB><<<grid_for(nRays, THREADS), THREADS, 0, ctx->stream>>>(
-        ctx->dCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm, 0, ctx->genericOctant);
+    k_extend_simple<DIV, kStack, THREADS, MINB><<<grid_for(nRays, THREADS), THREADS, 0, ctx->xStream>>>(
+        ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm, 0, ctx->genericOctant);
 }
 
 template <int K, int CH>
@@ -311,8 +329,8 @@ void launch_chunk_kc(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
     constexpr int THREADS = 128;
     const long long warps = (nRays + CH - 1) / CH;
-    k_extend_chunk<DIV_MARKSTEIN1, kStack, K, CH, THREADS, 10><<<grid_for(warps * 32, THREADS), THREADS, 0, ctx->stream>>>(
-        ctx->dCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, (uint32_t)nRays, ctx->sceneTame, perm, ctx->refill);
+    k_extend_chunk<DIV_MARKSTEIN1, kStack, K, CH, THREADS, 10><<<grid_for(warps * 32, THREADS), THREADS, 0, ctx->xStream>>>(
+        ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, (uint32_t)nRays, ctx->sceneTame, perm, ctx->refill);
 }
 
 template <int K>
@@ -338,8 +356,8 @@ void launch_simple(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 template <int FETCH>
 void launch_simple_tex(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
-    k_extend_simple<DIV_MARKSTEIN1, kStack, 128, 12, FETCH><<<grid_for(nRays, 128), 128, 0, ctx->stream>>>(
-        ctx->dCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm, ctx->pairsTex);
+    k_extend_simple<DIV_MARKSTEIN1, kStack, 128, 12, FETCH><<<grid_for(nRays, 128), 128, 0, ctx->xStream>>>(
+        ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm, ctx->pairsTex);
 }
 
 template <int DIV, int K, int HIST, int REFILL>
@@ -355,8 +373,8 @@ void launch_persist_r(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     long long blocks = (long long)perSm * ctx->prop.multiProcessorCount;
     long long needed = (nRays + THREADS - 1) / THREADS;
     if (blocks > needed) blocks = needed;
-    cudaMemsetAsync(ctx->dQueue, 0, sizeof(unsigned int), ctx->stream);
-    kern<<<(unsigned)blocks, THREADS, 0, ctx->stream>>>(ctx->dCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs,
+    cudaMemsetAsync(ctx->dQueue, 0, sizeof(unsigned int), ctx->xStream);
+    kern<<<(unsigned)blocks, THREADS, 0, ctx->xStream>>>(ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs,
                                                         ctx->rootRef, (uint32_t)nRays, ctx->sceneTame, ctx->dQueue, perm);
 }
 
@@ -524,6 +542,17 @@ int uvrt_create(uvrt_ctx** out, int device)
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         e = cudaStreamCreateWithPriority(&ctx->genStream, cudaStreamNonBlocking, hi);
     }
+    for (int k = 0; k < 2; k++) {
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->extStream[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->extDone[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->accDone[k], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->forkEv, cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&ctx->accStream, cudaStreamNonBlocking, hi);
+    }
     for (RaySlot& r : ctx->slots) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.genDone, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.freeEv, cudaEventDisableTiming);
@@ -545,7 +574,16 @@ void uvrt_destroy(uvrt_ctx* ctx)
     if (!ctx) return;
     Bind b(ctx);
     if (ctx->genStream) cudaStreamSynchronize(ctx->genStream);
+    for (int k = 0; k < 2; k++) if (ctx->extStream[k]) cudaStreamSynchronize(ctx->extStream[k]);
     cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->extStream[k]) cudaStreamDestroy(ctx->extStream[k]);
+        if (ctx->extDone[k]) cudaEventDestroy(ctx->extDone[k]);
+        if (ctx->accDone[k]) cudaEventDestroy(ctx->accDone[k]);
+    }
+    if (ctx->forkEv) cudaEventDestroy(ctx->forkEv);
+    if (ctx->accStream) { cudaStreamSynchronize(ctx->accStream); cudaStreamDestroy(ctx->accStream); }
+    if (ctx->dCountsAlt) cudaFree(ctx->dCountsAlt);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     void* ptrs[] = {ctx->dPairs, ctx->dWtris, ctx->dVerts, ctx->dCounts, ctx->dSum, ctx->dMax, ctx->dDose,
                     ctx->dColor, ctx->dQueue, ctx->dSeeds, ctx->dSeedPos, ctx->dFlush, ctx->dRawNodes, ctx->dRawIdx,
@@ -609,12 +647,14 @@ static int ensure_scene_buffers(uvrt_ctx* ctx, size_t pairBytes, size_t wtriByte
         ctx->nTris = 0;
         if ((rc = dev_alloc(ctx, &ctx->dVerts, (size_t)nTris * 4))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->dCounts, (size_t)nTris))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->dCountsAlt, (size_t)nTris))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->dSum, (size_t)nTris))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->dMax, (size_t)nTris))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->dDose, (size_t)nTris))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->dColor, (size_t)nTris * 9))) return rc;
         ctx->nTris = nTris;
         CK(cudaMemsetAsync(ctx->dCounts, 0, (size_t)nTris * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->dCountsAlt, 0, (size_t)nTris * 4, ctx->stream));
         CK(cudaMemsetAsync(ctx->dSum, 0, (size_t)nTris * 8, ctx->stream));
         CK(cudaMemsetAsync(ctx->dMax, 0, (size_t)nTris * 8, ctx->stream));
         CK(cudaMemsetAsync(ctx->dDose, 0, (size_t)nTris * 4, ctx->stream));
@@ -1054,6 +1094,7 @@ int uvrt_reset(uvrt_ctx* ctx, int resetColor)
         k_reset<<<grid_for(ctx->nTris, 256), 256, 0, ctx->stream>>>(ctx->dSum, ctx->dMax, ctx->dCounts, ctx->dColor,
                                                                      resetColor, ctx->nTris);
     }
+    CK(cudaMemsetAsync(ctx->dCountsAlt, 0, (size_t)ctx->nTris * 4, ctx->stream));
     ctx->launches++;
     CK_LAUNCH("reset");
     return UVRT_OK;
@@ -1112,6 +1153,8 @@ int uvrt_extend(uvrt_ctx* ctx, int64_t nRays)
     if (nRays == 0) return UVRT_OK;
     int rc;
     const uint32_t* perm = nullptr;
+    ctx->xStream = ctx->stream;
+    ctx->xCounts = ctx->dCounts;
     // a few thousand rays are not worth the extra launches
     if (ctx->binRays && nRays >= kMinRaysForBinning) {
         if (ctx->rs().permRays != nRays) {          // not already done on the generate stream
@@ -1183,9 +1226,77 @@ int uvrt_trace_counts(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLe
 int uvrt_trace(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, float duration, int64_t firstRay,
                int64_t nRays, uint32_t seedIn)
 {
-    int rc = uvrt_trace_counts(ctx, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
+    if (!ctx) return UVRT_ERR_INVALID;
+    if (!ctx->nTris) return fail(ctx, UVRT_ERR_NO_SCENE, "%s: no scene uploaded", __func__);
+    const bool foreign = ctx->mainForeign;
+    const int variant = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
+    const bool sharedQueue = variant >= 10 && variant < 25;   // variant B's global queue head is one per context
+    if (!ctx->pipeline || !ctx->overlapExtend || nRays <= 0 || sharedQueue) {
+        int rc = uvrt_trace_counts(ctx, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
+        if (rc) return rc;
+        return uvrt_accumulate(ctx, duration);
+    }
+    // Overlapped: generate + bin on the generate stream, extend on the slot's own stream into the slot's
+    // own count buffer, accumulate on the main stream.  Dependencies (events):
+    //   generate k   after extend k-2      (same ray slot)
+    //   extend k     after generate/bin k, after accumulate k-2 (it zeroes the slot's counts), and after
+    //                whatever other calls put on the main stream since the last trace (reset, upload, ...)
+    //   accumulate k after extend k; accumulates run in launch order on one (high-priority) stream, so the
+    //                f64 sums are formed in the reference's order; the main stream waits for each of them
+    // Extend k+1 therefore only waits for data, not for extend k: its blocks fill the SMs that extend k's
+    // last wave leaves idle.
+    Bind b(ctx);
+    ctx->slot ^= 1;
+    const int si = ctx->slot;
+    RaySlot& S = ctx->rs();
+    cudaStream_t es = ctx->extStream[si];
+    if (foreign) {
+        CK(cudaEventRecord(ctx->forkEv, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->extStream[0], ctx->forkEv, 0));
+        CK(cudaStreamWaitEvent(ctx->extStream[1], ctx->forkEv, 0));
+        CK(cudaStreamWaitEvent(ctx->accStream, ctx->forkEv, 0));
+        CK(cudaStreamWaitEvent(ctx->genStream, ctx->forkEv, 0));
+    }
+    if (S.inFlight) CK(cudaStreamWaitEvent(ctx->genStream, S.freeEv, 0));
+    int rc = generate_on(ctx, ctx->genStream, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
     if (rc) return rc;
-    return uvrt_accumulate(ctx, duration);
+    const uint32_t* perm = nullptr;
+    if (ctx->binRays && nRays >= kMinRaysForBinning) {
+        rc = bin_finish(ctx, nRays, ctx->genStream);
+        if (rc) return rc;
+        CK_LAUNCH("bin");
+        perm = S.dPerm;
+    }
+    CK(cudaEventRecord(S.genDone, ctx->genStream));
+    CK(cudaStreamWaitEvent(es, S.genDone, 0));
+    if (ctx->accUsed[si]) CK(cudaStreamWaitEvent(es, ctx->accDone[si], 0));
+    ctx->xStream = es;
+    ctx->xCounts = si ? ctx->dCountsAlt : ctx->dCounts;
+    {
+        StageTimer t(ctx, UVRT_STAGE_EXTEND, es);
+        rc = launch_extend(ctx, nRays, perm);
+    }
+    ctx->xStream = ctx->stream;
+    int* counts = ctx->xCounts;
+    ctx->xCounts = ctx->dCounts;
+    if (rc) return rc;
+    CK_LAUNCH("extend");
+    CK(cudaEventRecord(ctx->extDone[si], es));
+    CK(cudaEventRecord(S.freeEv, es));
+    S.inFlight = true;
+    ctx->extUsed[si] = true;
+    CK(cudaStreamWaitEvent(ctx->accStream, ctx->extDone[si], 0));
+    {
+        StageTimer t(ctx, UVRT_STAGE_ACCUMULATE, ctx->accStream);
+        k_accumulate<<<grid_for(ctx->nTris, 256), 256, 0, ctx->accStream>>>(ctx->dSum, ctx->dMax, counts, duration, ctx->nTris);
+    }
+    ctx->launches++;
+    CK_LAUNCH("accumulate");
+    CK(cudaEventRecord(ctx->accDone[si], ctx->accStream));
+    ctx->accUsed[si] = true;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->accDone[si], 0));   // everything later on the main stream sees the maps
+    ctx->mainForeign = false;    // (Bind set it) nothing but this trace's accumulate is new on the main stream
+    return UVRT_OK;
 }
 
 int uvrt_seed_chain(uvrt_ctx* ctx, const float* lightPos3, int nLaunches, float lightLength, uint32_t seedIn,
@@ -1282,6 +1393,9 @@ int uvrt_sync(uvrt_ctx* ctx)
     if (!ctx) return UVRT_ERR_INVALID;
     Bind b(ctx);
     CK(cudaStreamSynchronize(ctx->genStream));
+    CK(cudaStreamSynchronize(ctx->extStream[0]));
+    CK(cudaStreamSynchronize(ctx->extStream[1]));
+    CK(cudaStreamSynchronize(ctx->accStream));
     CK(cudaStreamSynchronize(ctx->stream));
     return UVRT_OK;
 }
@@ -1350,6 +1464,7 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
     else if (!strcmp(key, "generic_octant")) ctx->genericOctant = value;
     else if (!strcmp(key, "chunk")) ctx->chunk = value;
     else if (!strcmp(key, "pipeline")) ctx->pipeline = value;
+    else if (!strcmp(key, "overlap_extend")) ctx->overlapExtend = value;
     else if (!strcmp(key, "host_repack")) ctx->hostRepack = value;
     else if (!strcmp(key, "fetch_mode")) ctx->fetchMode = value;
     else if (!strncmp(key, "bin_", 4)) {
@@ -1382,6 +1497,7 @@ int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value)
     else if (!strcmp(key, "generic_octant")) *value = ctx->genericOctant;
     else if (!strcmp(key, "chunk")) *value = ctx->chunk;
     else if (!strcmp(key, "pipeline")) *value = ctx->pipeline;
+    else if (!strcmp(key, "overlap_extend")) *value = ctx->overlapExtend;
     else if (!strcmp(key, "host_repack")) *value = ctx->hostRepack;
     else if (!strcmp(key, "fetch_mode")) *value = ctx->fetchMode;
     else if (!strcmp(key, "bin_rays")) *value = ctx->binRays;
@@ -1399,12 +1515,22 @@ int uvrt_stage_time(uvrt_ctx* ctx, uvrt_stage stage, double* ms, int64_t* launch
     CK(cudaStreamSynchronize(ctx->stream));
     double sum = 0;
     int64_t n = 0;
+    // Launches of one stage may overlap (extend k+1 starts in the tail of extend k when "overlap_extend"
+    // is on): a launch is charged from the later of its own start and its predecessor's stop, so the sum
+    // is the time during which the stage was running at all.
+    const TimedLaunch* prev = nullptr;
     for (auto& t : ctx->timed) {
         if (t.stage != (int)stage) continue;
         float f = 0;
         CK(cudaEventElapsedTime(&f, t.start, t.stop));
+        if (prev) {
+            float ov = 0;
+            if (cudaEventElapsedTime(&ov, t.start, prev->stop) == cudaSuccess && ov > 0.0f) f -= std::min(ov, f);
+            else cudaGetLastError();
+        }
         sum += f;
         n++;
+        prev = &t;
     }
     if (ms) *ms = sum;
     if (launches) *launches = n;
