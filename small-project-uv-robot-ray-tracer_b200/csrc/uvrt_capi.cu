@@ -112,7 +112,7 @@ struct uvrt_ctx {
     uint32_t rootRef = 0;
     int sceneTame = 0;
     cudaTextureObject_t pairsTex = 0;   // the same buffer as a 1-D float4 texture ("fetch_mode" experiment)
-    int fetchMode = 0;
+    int fetchMode = 3;   // 3: rays, permutation kept out of L1 (ld.global.L1::no_allocate); 0: plain loads; 1/2: texture experiments; 4: + evict_last nodes
     float4* dPairs = nullptr;   // nPairs x 4 float4
     float4* dWtris = nullptr;   // nTris  x 4 float4 (leaf order: v0+tag, edge1, edge2, pad)
     float4* dVerts = nullptr;   // nTris  x 4 float4 (reference order and layout)
@@ -172,6 +172,7 @@ struct uvrt_ctx {
     int stageTiming = 0;
     int histMode = 0;
     int blocksPerSm = 0;      // 0: default for the variant
+    int carveout = -1;        // experiment: preferred shared-memory carveout (percent) of the extend kernel, -1 = driver default
     int genericOctant = 0;    // experiment: the one-thread-per-ray kernel without octant specialisation
     int chunk = 128;          // rays per warp of the chunk-persistent kernel
     int simpleCfg = 1;        // 128 threads, <= 40 registers (48 resident warps per SM): fastest in the sweep
@@ -356,6 +357,9 @@ void launch_simple(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 template <int FETCH>
 void launch_simple_tex(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
+    if (ctx->carveout >= 0) {
+        cudaFuncSetAttribute(k_extend_simple<DIV_MARKSTEIN1, kStack, 128, 12, FETCH>, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->carveout);
+    }
     k_extend_simple<DIV_MARKSTEIN1, kStack, 128, 12, FETCH><<<grid_for(nRays, 128), 128, 0, ctx->xStream>>>(
         ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm, ctx->pairsTex);
 }
@@ -470,6 +474,8 @@ int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     else if (v == 1) launch_simple<DIV_MARKSTEIN2>(ctx, nRays, perm);
     else if (v == 2 && ctx->fetchMode == 1 && ctx->pairsTex) launch_simple_tex<1>(ctx, nRays, perm);
     else if (v == 2 && ctx->fetchMode == 2 && ctx->pairsTex) launch_simple_tex<2>(ctx, nRays, perm);
+    else if (v == 2 && ctx->fetchMode == 3 && ctx->simpleCfg == 1) launch_simple_tex<3>(ctx, nRays, perm);
+    else if (v == 2 && ctx->fetchMode == 4) launch_simple_tex<4>(ctx, nRays, perm);
     else if (v == 2) launch_simple<DIV_MARKSTEIN1>(ctx, nRays, perm);
     else if (v >= 40 && v < 44) {
         // chunk-persistent warps (k_extend_chunk): K = {1, 2, 4, 8}[v - 40]; "refill", "chunk" options
@@ -1462,6 +1468,7 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
     else if (!strcmp(key, "refill")) ctx->refill = value;
     else if (!strcmp(key, "simple_cfg")) ctx->simpleCfg = value;
     else if (!strcmp(key, "generic_octant")) ctx->genericOctant = value;
+    else if (!strcmp(key, "carveout")) ctx->carveout = value;
     else if (!strcmp(key, "chunk")) ctx->chunk = value;
     else if (!strcmp(key, "pipeline")) ctx->pipeline = value;
     else if (!strcmp(key, "overlap_extend")) ctx->overlapExtend = value;

@@ -46,6 +46,28 @@ __device__ __forceinline__ W4 ldg256w(const float4* p)
     asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w0), "=l"(r.w1), "=l"(r.w2), "=l"(r.w3) : "l"(p));
     return r;
 }
+// cache-hint experiments ("fetch_mode" 3/4): nodes marked evict_last in L1, streaming data (rays,
+// permutation, results) kept out of L1
+__device__ __forceinline__ W4 ldg256w_keep(const float4* p)
+{
+    W4 r;
+    asm("ld.global.nc.L1::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w0), "=l"(r.w1), "=l"(r.w2), "=l"(r.w3) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ F8 ld256_stream(const float4* p)
+{
+    F8 r;
+    asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+        : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_u32_stream(const uint32_t* p)
+{
+    uint32_t r;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
 // Packed binary32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): each half is an ordinary IEEE round-to-nearest
 // operation, so results are bit-identical to the scalar forms at half the issue slots.
 __device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
@@ -462,6 +484,7 @@ __device__ __forceinline__ void bvh_intersect(RayCtx& ray, const float4* __restr
         W4 ca, cb;
         if (FETCH == 1) { ca = tex_w4(tex, cur * 4u); cb = tex_w4(tex, cur * 4u + 2u); }
         else if (FETCH == 2) { ca = ldg256w(p); cb = tex_w4(tex, cur * 4u + 2u); }
+        else if (FETCH == 4) { ca = ldg256w_keep(p); cb = ldg256w_keep(p + 2); }
         else { ca = ldg256w(p); cb = ldg256w(p + 2); }
         float t1, t2;
         const bool h1 = intersect_aabb<DIV, OCT>(ray, ca, t1);
@@ -537,9 +560,17 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_extend_simple(int* __res
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nRays) return;
-    if (perm) i = perm[i];
+    if (perm) i = FETCH >= 3 ? ldg_u32_stream(perm + i) : perm[i];
     RayCtx ray;
-    load_ray(rays, i, ray);
+    if (FETCH >= 3) {
+        F8 r = ld256_stream(rays + 2 * i);
+        ray.dx = r.lo.x; ray.dy = r.lo.y; ray.dz = r.lo.z;
+        ray.ox = r.lo.w; ray.oy = r.hi.x; ray.oz = r.hi.y;
+        ray.dist = r.hi.z;
+        ray.tri = __float_as_uint(r.hi.w);
+        ray.noXY = ray.noZZ = ray.rXY = ray.rZZ = ray.ndXY = ray.ndZZ = 0ull;
+    } else
+        load_ray(rays, i, ray);
     trace_one<DIV, STACK, FETCH>(ray, pairs, wtris, rootRef, sceneTame != 0, perm != nullptr && !genericOctant, tex);
     store_hit(rays, i, ray);
     if (ray.dist != kNoHit) atomicAdd(&counts[ray.tri], 1);

@@ -81,6 +81,7 @@ def main():
     ap.add_argument("--bin", default="16,32,128", help="device binning: 0 (off) or nY,nT,nP; ';'-separated")
     ap.add_argument("--sort", default="none", help="host-side orderings, ';'-separated (see sorted_rays)")
     ap.add_argument("--positions", default="0")
+    ap.add_argument("--opt", action="append", default=[], help="extra backend option key=value, repeatable")
     args = ap.parse_args()
 
     sim = uv.Sim(asset_root=os.path.join(ROOT, "data"))
@@ -89,6 +90,9 @@ def main():
     c = sim.ctx
     floor = sim.mesh_info()["floor"]
     p, pos, P = sim.params, sim.positions, args.rays
+    for kv in args.opt:
+        k, v = kv.split("=")
+        c.set_option(k, int(v))
     print(json.dumps({"device": c.device_info(), "scene": c.scene_info()}))
     for pi in ints(args.positions):
         lp = (np.float32(pos[pi, 0]), np.float32(np.float32(floor) + np.float32(p.lightHeight)), np.float32(pos[pi, 1]))
@@ -141,7 +145,7 @@ def main():
                                   "cfg": cfg, "fetch": fetch, "chunk": chunk, "generic": generic, "ms_best": round(best, 4),
                                   "ms_med": round(float(np.median(times)), 4), "mrays_s": round(P / best / 1e3, 1),
                                   "counts_equal": bool(np.array_equal(counts, ref_counts))}), flush=True)
-    for k, v in (("extend_variant", -1), ("bin_rays", 1), ("hist_mode", 0), ("fetch_mode", 0), ("simple_cfg", 1), ("refill", 24), ("chunk", 128), ("generic_octant", 0)):
+    for k, v in (("extend_variant", -1), ("bin_rays", 1), ("hist_mode", 0), ("fetch_mode", 3), ("simple_cfg", 1), ("refill", 24), ("chunk", 128), ("generic_octant", 0)):
         c.set_option(k, v)
 
 
