@@ -540,3 +540,90 @@ def test_device_scene_repack_equals_host_repack(uv, room):
         assert h[3] == d[3], f"scene {k}: leaf triangles differ"
         assert d[4] < h[4]                                       # raw arrays are smaller than the repacked image
     assert images[0][-1][1] == 0 and images[0][0][1] == 1
+
+
+def test_full_default_run_bookkeeping(uv, room):
+    """BASELINE configs[1] at full size -- route.xml, 2^25 photons x 10 iterations = 335,544,240 rays, far
+    beyond what the oracle traces in seconds -- checked through properties that do not depend on size:
+    the maps the RayTracer run leaves behind equal, bit for bit, the f64 sums / maxima formed on the host
+    from per-launch integer counts (same SEED chain, launched one by one through the stage API); every
+    ray that reports a hit was counted exactly once; the dose inverts back to the photon map."""
+    tris, nodes, tri_idx, floor = room
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_mesh("testroomopt")
+    sim.init("route")
+    p = sim.params
+    assert p.photonCount == 1 << 25 and p.maxIterations == 10 and len(sim.positions) == 12
+    seed0 = p.seedState
+    dose = sim.run()
+    c = sim.ctx
+    got_sum, got_max = c.read(uv.BUF.SUM), c.read(uv.BUF.MAX)
+    assert sim.rays_traced() == 335_544_240 and sim.params.photonMapSize == 335_544_240
+    seed_end = sim.params.seedState
+    positions = np.array(sim.positions, dtype=np.float32).copy()
+    sim.close()
+
+    c2 = uv.Context(0)
+    c2.upload_scene(tris, nodes, tri_idx)
+    P = int(p.photonsPerLight)
+    f32 = np.float32
+    want_sum, want_max = np.zeros(tris.shape[0]), np.zeros(tris.shape[0])
+    seed, total_hits = seed0, 0
+    for it in range(10):
+        for k, (x, y, dur) in enumerate(positions):
+            lp = (f32(x), f32(f32(floor) + f32(p.lightHeight)), f32(y))
+            c2.reset(False)
+            c2.trace_counts(lp, p.lightLength, 0, P, seed)
+            counts = c2.read(uv.BUF.COUNTS)
+            if it in (0, 9) and k in (0, 11):
+                rays = c2.read(uv.BUF.RAYS, P)        # 89 MB: only a few launches
+                hit = rays["dist"] != f32(1e30)
+                assert int(hit.sum()) == int(counts.sum())
+                assert np.array_equal(np.bincount(rays["triID"][hit], minlength=len(counts)), counts)
+            total_hits += int(counts.sum())
+            want_sum += counts.astype(np.float64) * np.float64(f32(dur))
+            want_max = np.maximum(want_max, counts.astype(np.float64))
+            seed = int(c2.seed_chain([lp], p.lightLength, seed)[-1])
+    c2.close()
+    assert seed == seed_end
+    assert got_sum.tobytes() == want_sum.tobytes() and got_max.tobytes() == want_max.tobytes()
+    assert 0.85 < total_hits / 335_544_240 < 1.0
+    # computeDosage (shade.cl:23-41) inverted: dose * area * photonsPerLight / (I * 0.1) == photon map
+    v0, v1, v2 = (tris[:, 0:3].astype(np.float64), tris[:, 4:7].astype(np.float64), tris[:, 8:11].astype(np.float64))
+    area = 0.5 * np.linalg.norm(np.cross(v0 - v1, v0 - v2), axis=1)
+    ok = area > 1e-12
+    back = dose[ok].astype(np.float64) * area[ok] * (335_544_240 // 12) / (np.float64(f32(p.lightIntensity)) * 0.1)
+    assert np.allclose(back, want_sum[ok], rtol=2e-5, atol=1e-6)
+
+
+def test_soup_scene_config5(uv):
+    """BASELINE config 5 (incoherent traversal stress), reduced to 1 M triangles: device-built BVH,
+    binned and unbinned extend bit-identical to the oracle on the rays the oracle can afford, integer
+    counts independent of the ray order, tree deeper than any room (depth > 21)."""
+    import sys as _sys
+    _sys.path.insert(0, T.ROOT + "/tools")
+    from soup import make_soup, soup_route
+    c = uv.Context(0)
+    tris, nodes, tri_idx = c.build_bvh(make_soup(1_000_000))
+    c.upload_scene(tris, nodes, tri_idx)
+    info = c.scene_info()
+    assert info["inner"] + info["leaves"] <= len(nodes) and info["depth"] > 21 and c.get_option("scene_tame") == 1
+    x, z, _ = soup_route()[5]
+    lp = (np.float32(x), np.float32(0.5), np.float32(z))
+    P = 1_000_000
+    counts = []
+    for binned in (0, 1):
+        c.set_option("bin_rays", binned)
+        c.reset(False)
+        c.trace_counts(lp, 1.0, 0, P, 3)
+        counts.append(c.read(uv.BUF.COUNTS))
+    assert np.array_equal(counts[0], counts[1]) and 0.02 < counts[0].sum() / P < 0.9
+    n = 100_000
+    got = c.read(uv.BUF.RAYS, P)[:n]
+    O = T.oracle()
+    want = np.zeros(n, dtype=T.RAY_DT)
+    O.orc_generate(T.ptr(want), 0, n, lp[0], lp[1], lp[2], np.float32(1.0), 3, None)
+    temp = np.zeros(tris.shape[0], dtype=np.int32)
+    O.orc_extend(T.ptr(temp), T.ptr(tris), T.ptr(want), T.ptr(nodes), T.ptr(tri_idx), n, 0, None)
+    assert got.tobytes() == want.tobytes()
+    c.close()
