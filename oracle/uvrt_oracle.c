@@ -94,7 +94,9 @@ static inline uint32_t generate_one(orc_ray* out, int32_t tid, float lx, float l
         float fz = random_float(&seed) * 2.0f - 1.0f;
         x = (double)fx;
         z = (double)fz;
-    } while (x * x + z * z > 1.0);
+        /* WangHash(61) == 0 and xorshift32 never leaves 0: the reference's loop then never ends (a GPU
+         * hang).  Decision: such a work-item keeps its first draw. */
+    } while (x * x + z * z > 1.0 && seed != 0u);
     double scale = len / sqrt(x * x + z * z);                   /* generate.cl:29 */
     r.dirx = (float)(x * scale);
     r.diry = diry;

@@ -137,7 +137,10 @@ __device__ __forceinline__ uint32_t generate_ray(int gid, float lx, float ly, fl
         x = (double)fx;
         z = (double)fz;
         d2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(z, z));
-    } while (d2 > 1.0);
+        // WangHash(61) = 0, and xorshift32 never leaves 0: every draw is 0, (x, z) = (-1, -1) for ever and
+        // the reference's loop never ends (its GPU hangs until the watchdog fires: SURVEY App. B, DESIGN.md
+        // section 6).  Such a work-item keeps the values of its first pass: a ray straight down.
+    } while (d2 > 1.0 && seed != 0u);
     double scale = __ddiv_rn(len, __dsqrt_rn(d2));                          // generate.cl:29
     out.a = make_float4(__double2float_rn(__dmul_rn(x, scale)), diry,
                         __double2float_rn(__dmul_rn(z, scale)), lx);

@@ -627,3 +627,25 @@ def test_soup_scene_config5(uv):
     O.orc_extend(T.ptr(temp), T.ptr(tris), T.ptr(want), T.ptr(nodes), T.ptr(tri_idx), n, 0, None)
     assert got.tobytes() == want.tobytes()
     c.close()
+
+
+def test_generate_zero_rng_state_terminates(uv, ctx, room):
+    """The reference's generate kernel never returns for a work-item whose seed hashes to 0 (WangHash(61));
+    here that work-item keeps its first draw.  Same launch as tests/test_oracle.py's: bit-identical."""
+    f32 = np.float32
+    lp = (f32(0.0), f32(0.5), f32(np.linspace(-4, 4, 12, dtype=np.float32)[2]))
+    n = 4096
+    ctx.generate(lp, 1.0, 0, n, 2)
+    got = ctx.read(uv.BUF.RAYS, n)
+    O = T.oracle()
+    want = np.zeros(n, dtype=T.RAY_DT)
+    O.orc_generate(T.ptr(want), 0, n, lp[0], lp[1], lp[2], f32(1.0), 2, None)
+    assert got.tobytes() == want.tobytes()
+    assert got[5]["dir"].tobytes() == np.array([-0.0, -1.0, -0.0], dtype=np.float32).tobytes()
+    ctx.reset(False)
+    ctx.extend(n)                                   # an axis-parallel ray: literal IEEE path, no hang either
+    hit = ctx.read(uv.BUF.RAYS, n)
+    tris, nodes, tri_idx, _ = room
+    temp = np.zeros(tris.shape[0], dtype=np.int32)
+    O.orc_extend(T.ptr(temp), T.ptr(tris), T.ptr(want), T.ptr(nodes), T.ptr(tri_idx), n, 0, None)
+    assert hit.tobytes() == want.tobytes() and np.array_equal(ctx.read(uv.BUF.COUNTS), temp)

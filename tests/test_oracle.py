@@ -163,3 +163,30 @@ def test_reset(checkers):
     assert not pm.any() and not mx.any() and not t.any() and col.all()
     O.orc_reset(T.ptr(pm), T.ptr(mx), T.ptr(t), T.ptr(col), 1, n)
     assert not col.any()
+
+
+def test_zero_rng_state_does_not_hang(checkers):
+    """WangHash(61) == 0 and xorshift32 maps 0 to 0: a work-item whose seed expression evaluates to 61 draws
+    zeros for ever and the reference's rejection loop (generate.cl:25-28) never terminates -- a GPU hang in
+    the reference (found by the 10 M-triangle sweep: lamp (0, 0.5, -2.5454545), SEED 2, work-item 5).  The
+    port and the CUDA kernel keep the first draw instead: origin at the lamp's foot, direction straight down."""
+    O = T.oracle()
+    assert O.orc_wang_hash(61) == 0
+    f32 = np.float32
+    lp = (f32(0.0), f32(0.5), f32(np.linspace(-4, 4, 12, dtype=np.float32)[2]))
+    rays = np.zeros(16, dtype=T.RAY_DT)
+    so = C.c_uint32(7)
+    O.orc_generate(T.ptr(rays), 0, 16, lp[0], lp[1], lp[2], f32(1.0), 2, C.byref(so))
+    r = rays[5]
+    assert r["dir"].tobytes() == np.array([-0.0, -1.0, -0.0], dtype=np.float32).tobytes()
+    assert r["orig"].tobytes() == np.array(lp, dtype=np.float32).tobytes()
+    assert r["dist"] == f32(1e30) and r["triID"] == 0
+    assert np.all(np.abs(np.linalg.norm(rays["dir"].astype(np.float64), axis=1) - 1.0) < 1e-6)
+    # work-item 0 stuck at zero: SEED_out is 0 (lamp term 60: 0*17 + 1 + 60 = 61)
+    so = C.c_uint32(7)
+    O.orc_generate(T.ptr(rays), 0, 1, f32(0.0), f32(0.0), f32(60.0 / 11.0), f32(1.0), 0, C.byref(so))
+    e = f32(1.0) + f32(0.0) * f32(13.0)
+    e = f32(e + f32(0.0) * f32(7.0))
+    e = f32(e + f32(f32(60.0 / 11.0) * f32(11.0)))
+    if int(e) == 61:
+        assert so.value == 0
