@@ -116,6 +116,9 @@ struct uvrt_ctx {
     float4* dPairs = nullptr;   // nPairs x 4 float4
     float4* dWtris = nullptr;   // nTris  x 4 float4 (leaf order: v0+tag, edge1, edge2, pad)
     float4* dVerts = nullptr;   // nTris  x 4 float4 (reference order and layout)
+    float4* dVertsSpare = nullptr;   // upload target while the previous scene is still valid; swapped in on success
+    size_t vertsCap = 0, vertsSpareCap = 0;   // capacities in triangles
+    cudaEvent_t vertsEv = nullptr;
     // per-triangle state (raytracer.h:54-55)
     int* dCounts = nullptr;
     double* dSum = nullptr;
@@ -590,6 +593,8 @@ void uvrt_destroy(uvrt_ctx* ctx)
     if (ctx->forkEv) cudaEventDestroy(ctx->forkEv);
     if (ctx->accStream) { cudaStreamSynchronize(ctx->accStream); cudaStreamDestroy(ctx->accStream); }
     if (ctx->dCountsAlt) cudaFree(ctx->dCountsAlt);
+    if (ctx->dVertsSpare) cudaFree(ctx->dVertsSpare);
+    if (ctx->vertsEv) cudaEventDestroy(ctx->vertsEv);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     void* ptrs[] = {ctx->dPairs, ctx->dWtris, ctx->dVerts, ctx->dCounts, ctx->dSum, ctx->dMax, ctx->dDose,
                     ctx->dColor, ctx->dQueue, ctx->dSeeds, ctx->dSeedPos, ctx->dFlush, ctx->dRawNodes, ctx->dRawIdx,
@@ -649,9 +654,13 @@ static int ensure_scene_buffers(uvrt_ctx* ctx, size_t pairBytes, size_t wtriByte
         if ((rc = dev_alloc(ctx, &ctx->dWtris, wtriBytes / 16))) return rc;
         ctx->wtriCap = wtriBytes;
     }
+    if ((size_t)nTris > ctx->vertsCap) {
+        ctx->vertsCap = 0;
+        if ((rc = dev_alloc(ctx, &ctx->dVerts, (size_t)nTris * 4))) return rc;
+        ctx->vertsCap = (size_t)nTris;
+    }
     if (nTris != ctx->nTris) {
         ctx->nTris = 0;
-        if ((rc = dev_alloc(ctx, &ctx->dVerts, (size_t)nTris * 4))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->dCounts, (size_t)nTris))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->dCountsAlt, (size_t)nTris))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->dSum, (size_t)nTris))) return rc;
@@ -726,6 +735,15 @@ static int upload_scene_device(uvrt_ctx* ctx, const void* trisV, int nTris, cons
         ctx->prepBlocks = std::max(1, std::min(perSm, 8)) * ctx->prop.multiProcessorCount;   // all blocks resident
     }
     cudaStream_t st = ctx->stream;
+    const bool verbose = getenv("UVRT_UPLOAD_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tPhase = now();
+    auto phase = [&](const char* name) {
+        if (!verbose) return;
+        double t = now();
+        fprintf(stderr, "[uvrt_upload_scene] %-22s %8.1f us\n", name, t - tPhase);
+        tPhase = t;
+    };
     char* stage = (char*)ctx->hStage;
     Status* dSt = (Status*)ctx->dPrepStatus;
     Status* hSt = (Status*)ctx->hPrepStatus;
@@ -735,6 +753,7 @@ static int upload_scene_device(uvrt_ctx* ctx, const void* trisV, int nTris, cons
     // nodes + triIdx first: the tree walk needs nothing else and runs while the triangles are staged
     par_copy(stage, nodesV, nodeBytes);
     par_copy(stage + idxOff, triIdx, idxBytes);
+    phase("stage nodes+idx");
     CK(cudaMemcpyAsync(ctx->dRawNodes, stage, nodeBytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->dRawIdx, stage + idxOff, idxBytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->dPrepQueue, 0xff, (size_t)nNodes * 8, st));
@@ -746,8 +765,21 @@ static int upload_scene_device(uvrt_ctx* ctx, const void* trisV, int nTris, cons
                                         ctx->dPrepQueue, parent, arrive, subInner, subSlots, dSt);
     CK(cudaMemcpyAsync(hSt, dSt, sizeof(Status), cudaMemcpyDeviceToHost, st));
     ctx->launches += 2;
+    phase("enqueue copies+walk");
     par_copy(stage + vertOff, trisV, vertBytes);
+    // the triangles travel on the second stream, next to the walk, into a spare buffer: the previous
+    // scene stays intact until the new tree has been validated
+    if ((size_t)nTris > ctx->vertsSpareCap) {
+        ctx->vertsSpareCap = 0;
+        if ((rc = dev_alloc(ctx, &ctx->dVertsSpare, (size_t)nTris * 4))) return rc;
+        ctx->vertsSpareCap = (size_t)nTris;
+    }
+    if (!ctx->vertsEv) CK(cudaEventCreateWithFlags(&ctx->vertsEv, cudaEventDisableTiming));
+    CK(cudaMemcpyAsync(ctx->dVertsSpare, stage + vertOff, vertBytes, cudaMemcpyHostToDevice, ctx->genStream));
+    CK(cudaEventRecord(ctx->vertsEv, ctx->genStream));
+    phase("stage triangles");
     CK(cudaStreamSynchronize(st));
+    phase("wait for the walk");
     CK_LAUNCH("scene walk");
     const Status s = *hSt;
     switch (s.err) {
@@ -767,15 +799,19 @@ static int upload_scene_device(uvrt_ctx* ctx, const void* trisV, int nTris, cons
     const int nPairs = (int)s.nPairs;
     const unsigned long long nSlots = s.nSlots;
     const size_t pairBytes = (size_t)std::max(nPairs, 1) * 64, wtriBytes = (size_t)std::max<unsigned long long>(nSlots, 1) * 64;
+    std::swap(ctx->dVerts, ctx->dVertsSpare);
+    std::swap(ctx->vertsCap, ctx->vertsSpareCap);
     if ((rc = ensure_scene_buffers(ctx, pairBytes, wtriBytes, nTris))) return rc;
-    CK(cudaMemcpyAsync(ctx->dVerts, stage + vertOff, vertBytes, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamWaitEvent(st, ctx->vertsEv, 0));
     if (nPairs == 0) CK(cudaMemsetAsync(ctx->dPairs, 0, pairBytes, st));
     const uint32_t reachable = s.tail;
     k_prep_emit<<<grid_for(reachable, 256), 256, 0, st>>>((const RawNode*)ctx->dRawNodes, ctx->dRawIdx, ctx->dVerts, ctx->dPrepQueue,
                                                          reachable, parent, subInner, subSlots, ctx->dPairs, ctx->dWtris, dSt);
     CK(cudaMemcpyAsync(hSt, dSt, sizeof(Status), cudaMemcpyDeviceToHost, st));
     ctx->launches += 1;
+    phase("enqueue verts+emit");
     CK(cudaStreamSynchronize(st));   // the staging buffer may be reused right away
+    phase("wait for emit");
     CK_LAUNCH("scene emit");
     ctx->nPairs = nPairs;
     ctx->nLeaves = nPairs + 1;       // a binary tree

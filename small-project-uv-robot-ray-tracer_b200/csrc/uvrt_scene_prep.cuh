@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128) k_prep_walk(const RawNode* __restrict__ n
         while (e == kEmpty) {
             if (ld_u32(&st->done)) return;
             if (++spins > (1u << 24)) { set_error(st, PREP_TIMEOUT, i, 0, 0); return; }
-            __nanosleep(40);
+            __nanosleep(20);
             e = vq[i];
         }
         const uint32_t n = (uint32_t)e, depth = (uint32_t)(e >> 32);
@@ -87,10 +87,15 @@ __global__ void __launch_bounds__(128) k_prep_walk(const RawNode* __restrict__ n
             const uint32_t c0 = nd.leftFirst, c1 = nd.leftFirst + 1;
             if (c1 >= nNodes || c1 < c0) { set_error(st, PREP_NODE_RANGE, c1 < c0 ? c0 : (c0 >= nNodes ? c0 : c1), 0, 0); return; }
             if ((int)depth + 1 >= maxDepth) { set_error(st, PREP_DEPTH, depth + 1, 0, 0); return; }
-            if (atomicCAS(&parent[c0], kNone, n) != kNone) { set_error(st, PREP_TWICE, c0, 0, 0); return; }
-            if (atomicCAS(&parent[c1], kNone, n) != kNone) { set_error(st, PREP_TWICE, c1, 0, 0); return; }
-            __threadfence();
+            // three independent atomics in flight together (the level-to-level latency of this walk is what
+            // the upload waits for); queue slots reserved by a node that then fails stay empty, and `done`
+            // releases whoever waits for them
+            const uint32_t old0 = atomicCAS(&parent[c0], kNone, n);
+            const uint32_t old1 = atomicCAS(&parent[c1], kNone, n);
             const uint32_t pos = atomicAdd(&st->tail, 2u);
+            if (old0 != kNone) { set_error(st, PREP_TWICE, c0, 0, 0); return; }
+            if (old1 != kNone) { set_error(st, PREP_TWICE, c1, 0, 0); return; }
+            __threadfence();
             const unsigned long long d1 = (unsigned long long)(depth + 1) << 32;
             vq[pos] = d1 | c0;
             vq[pos + 1] = d1 | c1;
