@@ -145,6 +145,7 @@ struct uvrt_ctx {
     int* xCounts = nullptr;
     long long lastRays = 0;
     unsigned int* dQueue = nullptr;      // persistent-kernel work counter
+    unsigned int* dSmCursor = nullptr;   // per-SM chunk cursors of the SM-affine extend (fetch_mode 5), 2 x 1024
     uint32_t* dSeeds = nullptr;
     float* dSeedPos = nullptr;
     int seedCap = 0;
@@ -363,8 +364,14 @@ void launch_simple_tex(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     if (ctx->carveout >= 0) {
         cudaFuncSetAttribute(k_extend_simple<DIV_MARKSTEIN1, kStack, 128, 12, FETCH>, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->carveout);
     }
+    unsigned int* cursor = nullptr;
+    if (FETCH == 5) {
+        if (!ctx->dSmCursor) cudaMalloc((void**)&ctx->dSmCursor, 2 * 1024 * sizeof(unsigned int));
+        cursor = ctx->dSmCursor + 1024 * ctx->slot;          // one cursor table per ray slot: extends may overlap
+        cudaMemsetAsync(cursor, 0, 1024 * sizeof(unsigned int), ctx->xStream);
+    }
     k_extend_simple<DIV_MARKSTEIN1, kStack, 128, 12, FETCH><<<grid_for(nRays, 128), 128, 0, ctx->xStream>>>(
-        ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm, ctx->pairsTex);
+        ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm, ctx->pairsTex, 0, cursor);
 }
 
 template <int DIV, int K, int HIST, int REFILL>
@@ -479,6 +486,7 @@ int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     else if (v == 2 && ctx->fetchMode == 2 && ctx->pairsTex) launch_simple_tex<2>(ctx, nRays, perm);
     else if (v == 2 && ctx->fetchMode == 3 && ctx->simpleCfg == 1) launch_simple_tex<3>(ctx, nRays, perm);
     else if (v == 2 && ctx->fetchMode == 4) launch_simple_tex<4>(ctx, nRays, perm);
+    else if (v == 2 && ctx->fetchMode == 5 && perm) launch_simple_tex<5>(ctx, nRays, perm);
     else if (v == 2) launch_simple<DIV_MARKSTEIN1>(ctx, nRays, perm);
     else if (v >= 40 && v < 44) {
         // chunk-persistent warps (k_extend_chunk): K = {1, 2, 4, 8}[v - 40]; "refill", "chunk" options
@@ -597,7 +605,7 @@ void uvrt_destroy(uvrt_ctx* ctx)
     if (ctx->vertsEv) cudaEventDestroy(ctx->vertsEv);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     void* ptrs[] = {ctx->dPairs, ctx->dWtris, ctx->dVerts, ctx->dCounts, ctx->dSum, ctx->dMax, ctx->dDose,
-                    ctx->dColor, ctx->dQueue, ctx->dSeeds, ctx->dSeedPos, ctx->dFlush, ctx->dRawNodes, ctx->dRawIdx,
+                    ctx->dColor, ctx->dQueue, ctx->dSmCursor, ctx->dSeeds, ctx->dSeedPos, ctx->dFlush, ctx->dRawNodes, ctx->dRawIdx,
                     ctx->dPrepQueue, ctx->dPrepNode, ctx->dPrepStatus};
     if (ctx->hPrepStatus) cudaFreeHost(ctx->hPrepStatus);
     for (void* p : ptrs) if (p) cudaFree(p);

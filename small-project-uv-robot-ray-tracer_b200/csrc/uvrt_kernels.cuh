@@ -559,9 +559,37 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_extend_simple(int* __res
                                                        float4* __restrict__ rays, const float4* __restrict__ pairs,
                                                        uint32_t rootRef, long long nRays, int sceneTame,
                                                        const uint32_t* __restrict__ perm, cudaTextureObject_t tex = 0,
-                                                       int genericOctant = 0)
+                                                       int genericOctant = 0, unsigned int* __restrict__ smCursor = nullptr)
 {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long i;
+    if (FETCH == 5) {
+        // SM-affine chunks ("fetch_mode 5"): the binned ray order is cut into one contiguous range per SM
+        // and a block takes the next 128-ray chunk of the range of the SM it happens to run on, so the
+        // blocks resident on one SM work on neighbouring bins and share node lines in that SM's L1.  A
+        // block whose SM's range is used up steals from the other SMs' ranges (every block takes exactly
+        // one chunk, and there are as many chunks as blocks).
+        __shared__ unsigned int sChunk;
+        if (threadIdx.x == 0) {
+            unsigned int smid, nsm;
+            asm("mov.u32 %0, %%smid;" : "=r"(smid));
+            asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+            const unsigned int C = gridDim.x;
+            unsigned int chunk = 0xffffffffu;
+            for (unsigned int v = 0; v < nsm && chunk == 0xffffffffu; v++) {
+                const unsigned int s = (smid + v) % nsm;
+                const unsigned int lo = (unsigned int)(((unsigned long long)s * C) / nsm), hi = (unsigned int)(((unsigned long long)(s + 1) * C) / nsm);
+                if (hi == lo) continue;
+                if (*reinterpret_cast<volatile unsigned int*>(&smCursor[s]) >= hi - lo) continue;
+                const unsigned int c = atomicAdd(&smCursor[s], 1u);
+                if (c < hi - lo) chunk = lo + c;
+            }
+            sChunk = chunk;
+        }
+        __syncthreads();
+        if (sChunk == 0xffffffffu) return;
+        i = (long long)sChunk * blockDim.x + threadIdx.x;
+    } else
+        i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nRays) return;
     if (perm) i = FETCH >= 3 ? ldg_u32_stream(perm + i) : perm[i];
     RayCtx ray;
