@@ -17,8 +17,9 @@ of the run (inside the timed region).
             every step uploads the scene (Tri/BVHNode/triIdx arrays -> pinned staging -> device),
             resets the maps, traces, shades and reads the dose map back; wall clock
   roofline  extend kernel: algorithmic bytes B_ray = 44 + 64*I + 52*T per ray (I, T
-            measured by the oracle's traversal counters on this very workload) over the event-timed
-            average launch duration, against the measured HBM copy bandwidth
+            measured by the oracle's traversal counters on this very workload and committed in
+            profiles/traversal_stats_route.json) over the event-timed average launch duration
+            (overlapping launches charged once), against the measured HBM copy bandwidth
   cpu_baseline  the reference's own kernels (oracle/_ref, compiled from its sources) or the C port,
             OpenMP over all host cores, on one pass over the route
 
@@ -213,6 +214,7 @@ def main():
     ap.add_argument("--impl", default="uvrt", choices=["uvrt", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--write-traversal-stats", action="store_true", help="re-measure I and T with the oracle's counters and commit them")
     ap.add_argument("--variant", type=int, default=-1)
     ap.add_argument("--opt", action="append", default=[], help="backend option key=value (uvrt_set_option), repeatable")
     args = ap.parse_args()
@@ -359,7 +361,18 @@ def main():
 
     # ---- roofline of the dominant kernel (extend) ----
     peak, peak_src = load_peaks()
-    I, T_ = traversal_stats(room, pos, p)
+    # I, T of SURVEY 8(d): measured once by the oracle's traversal counters on this workload and committed
+    # (profiles/traversal_stats_route.json, written by `python bench.py --write-traversal-stats`)
+    spath = os.path.join(ROOT, "profiles", "traversal_stats_route.json")
+    if args.write_traversal_stats or not os.path.exists(spath):
+        I, T_ = traversal_stats(room, pos, p)
+        if args.write_traversal_stats:
+            json.dump({"workload": WORKLOAD, "inner_visits_per_ray": I, "tri_tests_per_ray": T_,
+                       "source": "oracle/uvrt_oracle.c traversal counters, 12 positions x 200,000 rays of route.xml on testroomopt.glb"},
+                      open(spath, "w"), indent=1)
+    else:
+        st = json.load(open(spath))
+        I, T_ = float(st["inner_visits_per_ray"]), float(st["tri_tests_per_ray"])
     b_ray = 44.0 + 64.0 * I + 52.0 * T_
     ext_launch_ms = ext_ms / max(1, ext_n)
     achieved = b_ray * P / (ext_launch_ms * 1e-3) / 1e9
@@ -398,7 +411,8 @@ def main():
         "route_dose_map": "route.xml as shipped: 10 iterations x 12 positions x 2,796,202 rays, ResetDosageMap .. dose map on the host, wall clock, max over ranks",
         "dose_checksum": {"mean": float(np.mean(dose, dtype=np.float64)), "max": float(dose.max())},
     }
-    if not args.no_cpu:
+    if not args.no_cpu and n_gpus == 1:
+        # (rank 0, N = 1 only: under torchrun the host threads are shared with the other ranks)
         # bounded CPU sample: exactly one step of the GPU workload (one pass over the route)
         per_launch = P
         dt, rays, kind, cores, _, _ = cpu_route_pass(room, pos, p, per_launch)
