@@ -212,7 +212,7 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="uvrt", choices=["uvrt", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--write-traversal-stats", action="store_true", help="re-measure I and T with the oracle's counters and commit them")
     ap.add_argument("--variant", type=int, default=-1)
