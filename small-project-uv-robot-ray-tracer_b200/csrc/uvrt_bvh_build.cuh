@@ -195,8 +195,12 @@ __global__ void k_init_root(BNode* __restrict__ nodes, const uint32_t* __restric
 
 // Sweep over the 7 planes of every axis and the split decision (bvh.cpp:130-150, 52-54, 64-66): host
 // arithmetic in host order.  cnt[3][8]; lo/hi[3][8][3] order-encoded (empty bins keep the sentinels).
-__device__ __forceinline__ bool decide_split(const uint32_t* cnt, const uint32_t* lo, const uint32_t* hi, const BNode& nd,
-                                             int& axisOut, int& planeOut, uint32_t& Lout)
+// Returns 1 = split, 0 = leaf, 2 = leaf whose index segment the reference has already permuted: its
+// in-place partition loop runs before the "one side is empty" check (bvh.cpp:56-66), and with every element
+// on the right the loop leaves the segment rotated left by one.  (Only reachable when the costs degenerate
+// to inf / NaN, e.g. coordinates beyond 1e19; with every element on the left nothing moves.)
+__device__ __forceinline__ int decide_split(const uint32_t* cnt, const uint32_t* lo, const uint32_t* hi, const BNode& nd,
+                                            int& axisOut, int& planeOut, uint32_t& Lout)
 {
     float best = 1e30f;
     int axis = 0, plane = 0;
@@ -233,14 +237,21 @@ __device__ __forceinline__ bool decide_split(const uint32_t* cnt, const uint32_t
         }
     }
     const float noSplit = fm(half_area(nd.bmin, nd.bmax), __uint2float_rn(nd.count));
-    bool split = !(best >= noSplit);
+    int split = !(best >= noSplit) ? 1 : 0;
     uint32_t L = 0;
     if (split) {
         for (int b = 0; b < plane; b++) L += cnt[axis * kBins + b];
-        if (L == 0 || L == nd.count) split = false;
+        if (L == nd.count) split = 0;
+        else if (L == 0) split = 2;
     }
     axisOut = axis; planeOut = plane; Lout = L;
     return split;
+}
+
+// segment of a leaf into the final index array; `rotated`: see decide_split
+__device__ __forceinline__ uint32_t leaf_source(uint32_t first, uint32_t count, uint32_t i, bool rotated)
+{
+    return first + (rotated ? (i + 1 == count ? 0u : i + 1u) : i);
 }
 
 // per-thread bounds of the two children while placing: [lo hi clo chi] x {left, right}
@@ -350,9 +361,9 @@ __global__ void __launch_bounds__(THREADS) k_level(const uint32_t* __restrict__ 
     if (tid == 0) {
         int axis, plane;
         uint32_t L;
-        const bool split = decide_split(bins.cnt, bins.lo, bins.hi, nd, axis, plane, L);
+        const int split = decide_split(bins.cnt, bins.lo, bins.hi, nd, axis, plane, L);
         sAxis = axis; sPlane = plane; sSplit = split; sL = L;
-        if (split) {
+        if (split == 1) {
             const uint32_t child = atomicAdd(&q.counters[0], 2u);
             sChild = child;
             enqueue_child(child, first, L, q);
@@ -361,9 +372,9 @@ __global__ void __launch_bounds__(THREADS) k_level(const uint32_t* __restrict__ 
     }
     __syncthreads();
 
-    if (!sSplit) {
+    if (sSplit != 1) {
         // leaf: its segment is final
-        for (uint32_t i = tid; i < count; i += THREADS) finalIdx[first + i] = src[first + i];
+        for (uint32_t i = tid; i < count; i += THREADS) finalIdx[first + i] = src[leaf_source(first, count, i, sSplit == 2)];
         return;
     }
 
@@ -525,9 +536,10 @@ __global__ void __launch_bounds__(32) k_huge_decide(const HugeInfo* __restrict__
     HugeState& h = st[s];
     int axis, plane;
     uint32_t L;
-    const bool split = decide_split(h.cnt, h.lo, h.hi, nd, axis, plane, L);
-    h.axis = (uint32_t)axis; h.plane = (uint32_t)plane; h.split = split ? 1u : 0u; h.L = L; h.h = 0;
-    if (split) {
+    const int split = decide_split(h.cnt, h.lo, h.hi, nd, axis, plane, L);
+    h.axis = (uint32_t)axis; h.plane = (uint32_t)plane; h.split = split == 1 ? 1u : 0u; h.L = L; h.h = 0;
+    h.pad0 = split == 2 ? 1u : 0u;      // leaf with a rotated segment
+    if (split == 1) {
         const uint32_t child = atomicAdd(&q.counters[0], 2u);
         h.child = child;
         enqueue_child(child, hi_.first, L, q);
@@ -652,7 +664,7 @@ __global__ void __launch_bounds__(256) k_huge_place(const HugeInfo* __restrict__
     UVRT_HUGE_CHUNK_PROLOGUE()
     HugeState& h = st[slot];
     if (!h.split) {
-        for (uint32_t i = c0 + tid; i < c1; i += 256) finalIdx[first + i] = src[first + i];
+        for (uint32_t i = c0 + tid; i < c1; i += 256) finalIdx[first + i] = src[leaf_source(first, count, i, h.pad0 != 0)];
         return;
     }
     SplitTest test;
@@ -782,7 +794,11 @@ __global__ void __launch_bounds__(128) k_level_small(const uint32_t* __restrict_
             if (bin_of(c, lo, sc) < plane) i++;
             else { const uint32_t t = idx[i]; idx[i] = idx[j]; idx[j] = t; j--; }
         }
-        if (i == 0 || i == (int)count) split = false;   // (the swap loop only permuted a copy)
+        if (i == 0 || i == (int)count) {
+            // abandoned after the partition loop ran: the reference keeps the permuted order (bvh.cpp:56-66)
+            for (uint32_t k = 0; k < count; k++) finalIdx[first + k] = idx[k];
+            return;
+        }
     }
     if (!split) {
         for (uint32_t k = 0; k < count; k++) finalIdx[first + k] = src[first + k];

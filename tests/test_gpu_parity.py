@@ -420,6 +420,24 @@ def test_device_bvh_build_equals_host_builder(uv, ctx, room):
         _same_tree(ctx.build_bvh(m), B.build_bvh(m))
     soup = make_soup(200_000)
     _same_tree(ctx.build_bvh(soup), B.build_bvh(soup))
+    # a node of 40,000 identical triangles cannot be split: a leaf larger than the multi-block threshold
+    same = np.tile(soup[:1], (40_000, 1))
+    same = np.concatenate([same, soup[1:3000]])
+    _same_tree(ctx.build_bvh(same), B.build_bvh(same))
+    # exponentially spaced triangles: every split peels off a few of them, the tree is a deep comb
+    deep = soup[:300].copy()
+    scale = (np.float32(1.17) ** np.arange(300, dtype=np.float32))[:, None]
+    for k in range(3):
+        deep[:, 4 * k: 4 * k + 3] *= scale
+    td, nd, idd = ctx.build_bvh(deep)
+    _same_tree((td, nd, idd), B.build_bvh(deep))
+    c2 = uv.Context(0)
+    try:
+        c2.upload_scene(td, nd, idd)
+        assert c2.scene_info()["depth"] < 64
+    except uv.UvrtError as e:                     # deeper than the traversal stack: rejected, not mis-traversed
+        assert "depth" in str(e)
+    c2.close()
 
 
 def test_raytracer_with_device_built_bvh(uv, room, golden):
