@@ -622,7 +622,8 @@ def test_soup_scene_config5(uv):
     _sys.path.insert(0, T.ROOT + "/tools")
     from soup import make_soup, soup_route
     c = uv.Context(0)
-    tris, nodes, tri_idx = c.build_bvh(make_soup(1_000_000))
+    n_tris = int(os.environ.get("UVRT_SOUP_TRIS", "1000000"))     # 10000000 = the full config (oracle: ~1 Mrays/s)
+    tris, nodes, tri_idx = c.build_bvh(make_soup(n_tris))
     c.upload_scene(tris, nodes, tri_idx)
     info = c.scene_info()
     assert info["inner"] + info["leaves"] <= len(nodes) and info["depth"] > 21 and c.get_option("scene_tame") == 1

@@ -1,9 +1,11 @@
 """Incoherent-traversal stress (BASELINE.json config 5): synthetic triangle soup, ray sweep.
 
-    python tools/soup_bench.py --tris 1000000 --rays 1000000,10000000 [--check]
+    python tools/soup_bench.py --tris 1000000 --rays 1000000,10000000
+
+(The comparison with the oracle lives in tests/test_gpu_parity.py::test_soup_scene_config5; set
+UVRT_SOUP_TRIS=10000000 to run it at full size.)
 """
 import argparse
-import ctypes as C
 import importlib
 import json
 import os
@@ -25,7 +27,6 @@ def main():
     ap.add_argument("--tris", type=int, default=1_000_000)
     ap.add_argument("--size", type=float, default=0.01)
     ap.add_argument("--rays", default="1000000")
-    ap.add_argument("--check", action="store_true", help="compare one launch with the oracle (CPU)")
     args = ap.parse_args()
     t0 = time.perf_counter()
     tris = make_soup(args.tris, args.size)
@@ -63,25 +64,6 @@ def main():
             best = min(times[1:])
             print(json.dumps({"rays": P, "bin_rays": binned, "ms": round(best, 3), "mrays_s": round(P / best / 1e3, 1),
                               "hits": int(counts.sum())}), flush=True)
-        if args.check:
-            import uvrt_testlib as T
-            t, nodes, tri_idx = sim.mesh_data()
-            n = min(P, 200_000)
-            O = T.oracle()
-            rays = np.zeros(n, dtype=T.RAY_DT)
-            O.orc_generate(T.ptr(rays), 0, n, lp[0], lp[1], lp[2], 1.0, 0, None)
-            temp = np.zeros(t.shape[0], dtype=np.int32)
-            cnt = T.Counters()
-            tc = time.perf_counter()
-            O.orc_extend(T.ptr(temp), T.ptr(t), T.ptr(rays), T.ptr(nodes), T.ptr(tri_idx), n, 0, C.byref(cnt))
-            tc = time.perf_counter() - tc
-            ctx.reset(False)
-            ctx.trace_counts(lp, 1.0, 0, n, 0)
-            got = ctx.read(uv.BUF.RAYS, n)
-            ok = got.tobytes() == rays.tobytes() and np.array_equal(ctx.read(uv.BUF.COUNTS), temp)
-            print(json.dumps({"check_rays": n, "bit_identical_to_oracle": bool(ok), "oracle_mrays_s": round(n / tc / 1e6, 3),
-                              "inner_visits_per_ray": round(cnt.innerVisits / n, 2), "tri_tests_per_ray": round(cnt.triTests / n, 2),
-                              "max_stack": int(cnt.maxStack)}), flush=True)
 
 
 if __name__ == "__main__":
