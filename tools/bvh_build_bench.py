@@ -14,7 +14,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 uv = importlib.import_module("small-project-uv-robot-ray-tracer_b200")
 B = importlib.import_module("small-project-uv-robot-ray-tracer_b200.binding")
@@ -48,7 +47,6 @@ def main():
     ap.add_argument("--soup", default="1000000,10000000")
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
-    import uvrt_testlib as T
     sim = uv.Sim(asset_root=os.path.join(ROOT, "data"))
     sim.load_mesh("testroomopt")
     tris = sim.mesh_data()[0].copy()

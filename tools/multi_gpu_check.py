@@ -6,7 +6,7 @@
 Every rank traces its share of the launches (launches dealt by RayTracer::ShardOwner),
 the per-GPU maps are combined by uvrt_reduce (one NCCL all-reduce: sum of the photon map, max of
 the max map), and the result must equal -- bit for bit -- what rank 0 gets by running all launches
-alone, and the oracle's dose."""
+alone."""
 import importlib
 import os
 import sys
@@ -17,7 +17,6 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 uv = importlib.import_module("small-project-uv-robot-ray-tracer_b200")
 B = importlib.import_module("small-project-uv-robot-ray-tracer_b200.binding")
 

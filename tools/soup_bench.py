@@ -16,7 +16,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 uv = importlib.import_module("small-project-uv-robot-ray-tracer_b200")
 from soup import make_soup, soup_route  # noqa: E402
