@@ -15,13 +15,14 @@ static void usage()
            "                [--device-bvh] [--checkpoint FILE] [--resume FILE]\n"
            "  --export BASE      BASE.dose.f32, BASE.ply (per-vertex heat-map colours), BASE.json\n"
            "  --device-bvh       build the BVH on the GPU (uvrt_build_bvh) instead of on the host cores\n"
-           "  --checkpoint FILE  rewrite FILE after every iteration; --resume FILE continues such a run\n");
+           "  --checkpoint FILE  rewrite FILE after every iteration; --resume FILE continues such a run\n"
+           "  --json             one JSON line at the end: rays, wall and per-stage device times, Mrays/s\n");
 }
 
 int main(int argc, char** argv)
 {
     std::string room = "testroomopt", route = "route", out, exportBase, checkpoint, resume;
-    bool deviceBvh = false;
+    bool deviceBvh = false, jsonLine = false;
     int iterations = -1, photons = -1, device = 0, variant = -1;
     bool maxPower = false;
     for (int i = 1; i < argc; i++) {
@@ -40,6 +41,7 @@ int main(int argc, char** argv)
         else if (a == "--checkpoint") checkpoint = next();
         else if (a == "--resume") resume = next();
         else if (a == "--device-bvh") deviceBvh = true;
+        else if (a == "--json") jsonLine = true;
         else { usage(); return a == "--help" ? 0 : 2; }
     }
     Mesh mesh;
@@ -59,6 +61,7 @@ int main(int argc, char** argv)
     if (variant >= 0) uvrt_set_option(rayTracer.ctx, "extend_variant", variant);
     if (maxPower) rayTracer.viewMode = maxpower;
 
+    if (jsonLine) uvrt_set_option(rayTracer.ctx, "stage_timing", 1);
     rayTracer.ResetDosageMap();
     if (!resume.empty() && !rayTracer.LoadCheckpoint(resume.c_str())) { fprintf(stderr, "%s\n", rayTracer.lastError.c_str()); return 1; }
     while (rayTracer.ok) {
@@ -85,6 +88,24 @@ int main(int argc, char** argv)
     printf("triangles %d  rays %lld  mean %s %.6g  max %.6g  (%.1f Mrays/s wall)\n", mesh.triangleCount,
            (long long)rayTracer.RaysTraced(), maxPower ? "irradiance" : "dose", sum / mesh.triangleCount, mx,
            rayTracer.RaysTraced() / (rayTracer.compTime * 1e6));
+    if (jsonLine) {
+        static const char* names[] = {"generate", "extend", "accumulate", "shade", "color", "reset", "bin"};
+        char dev[128] = "";
+        int sms = 0, ccMajor = 0, ccMinor = 0;
+        uvrt_device_info(rayTracer.ctx, dev, sizeof dev, &sms, &ccMajor, &ccMinor);
+        printf("{\"room\": \"%s\", \"route\": \"%s\", \"device\": \"%s\", \"triangles\": %d, \"positions\": %d, \"iterations\": %d, "
+               "\"rays\": %lld, \"wall_ms\": %.3f, \"mrays_s_wall\": %.1f, \"kernel_launches\": %lld, \"stage_ms\": {",
+               room.c_str(), route.c_str(), dev, mesh.triangleCount, (int)rayTracer.lightPositions.size(), rayTracer.currIterations,
+               (long long)rayTracer.RaysTraced(), rayTracer.compTime * 1000.0f, rayTracer.RaysTraced() / (rayTracer.compTime * 1e6),
+               (long long)uvrt_launch_count(rayTracer.ctx));
+        for (int k = 0; k < 7; k++) {
+            double ms = 0;
+            int64_t n = 0;
+            uvrt_stage_time(rayTracer.ctx, (uvrt_stage)k, &ms, &n);
+            printf("%s\"%s\": %.3f", k ? ", " : "", names[k], ms);
+        }
+        printf("}, \"mean\": %.6g, \"max\": %.6g}\n", sum / mesh.triangleCount, mx);
+    }
     if (!exportBase.empty() && !rayTracer.SaveDosageMap(exportBase.c_str())) { fprintf(stderr, "%s\n", rayTracer.lastError.c_str()); return 1; }
     if (!out.empty()) {
         std::ofstream f(out, std::ios::binary);

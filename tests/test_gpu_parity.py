@@ -6,6 +6,7 @@ equal for EVERY ray and per-triangle counts integer-equal; accumulate / computeD
 dosageToColor / reset bit-equal (stricter than the 1-ulp allowance); end-to-end dose within
 rel. 1e-3 (north_star) -- and in fact bit-equal, which is asserted too."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -668,3 +669,36 @@ def test_generate_zero_rng_state_terminates(uv, ctx, room):
     temp = np.zeros(tris.shape[0], dtype=np.int32)
     O.orc_extend(T.ptr(temp), T.ptr(tris), T.ptr(want), T.ptr(nodes), T.ptr(tri_idx), n, 0, None)
     assert hit.tobytes() == want.tobytes() and np.array_equal(ctx.read(uv.BUF.COUNTS), temp)
+
+
+def test_headless_driver_cli(uv, golden, tmp_path):
+    """uvrt_cli = MyApp::Init + MyApp::Tick without the window (myapp.cpp:15-40, 156-175): one iteration of
+    lange_route with the device-built BVH must give the golden dose; --checkpoint/--resume, --export and the
+    --json metrics line work from the command line."""
+    import json
+    import subprocess
+    exe = os.path.join(uv.build_dir(), "uvrt_cli")
+    base = [exe, "--root", T.DATA, "--room", "testroomopt", "--route", "lange_route"]
+    out = tmp_path / "dose.f32"
+    r = subprocess.run(base + ["--iterations", "1", "--device-bvh", "--out", str(out), "--export", str(tmp_path / "room"), "--json"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    dose = np.fromfile(out, dtype=np.float32)
+    assert f"{T.fnv(dose):016x}" == golden["pass_lange_route"]["fnv_dose"]
+    assert "Progress: 100%" in r.stdout and "device build" in r.stdout
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["rays"] == 12 * 2796202 and line["triangles"] == 44866 and line["stage_ms"]["extend"] > 0
+    assert (tmp_path / "room.ply").exists() and (tmp_path / "room.json").exists()
+    assert np.fromfile(tmp_path / "room.dose.f32", dtype=np.float32).tobytes() == dose.tobytes()
+    # two iterations at once == one iteration + checkpoint, then a resumed process for the second
+    two = tmp_path / "two.f32"
+    ck = tmp_path / "run.ckpt"
+    resumed = tmp_path / "resumed.f32"
+    for args in (["--iterations", "2", "--out", str(two)],
+                 ["--iterations", "1", "--checkpoint", str(ck)],
+                 ["--iterations", "2", "--resume", str(ck), "--out", str(resumed)]):
+        r = subprocess.run(base + ["--photons", str(1 << 21)] + args, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    assert np.fromfile(two, dtype=np.float32).tobytes() == np.fromfile(resumed, dtype=np.float32).tobytes()
+    bad = subprocess.run(base[:3] + ["--room", "no_such_room"], capture_output=True, text=True, timeout=60)
+    assert bad.returncode == 1 and "cannot load room" in bad.stderr
