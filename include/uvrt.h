@@ -139,8 +139,21 @@ int uvrt_reduce(uvrt_ctx* ctx);
 int uvrt_reduce_counts(uvrt_ctx* ctx);
 
 /* ---- tuning and measurement ------------------------------------------------------------- */
-/* Options: "extend_variant" (kernel selection), "bin_rays" (0/1),
- * "stage_timing" (0/1: bracket every launch with CUDA events on the context's stream). */
+/* Options (defaults are the measured best; everything else exists for A/B runs, see DESIGN.md section 4 and
+ * profiles/r1_sweeps.md):
+ *   "extend_variant"  kernel selection: 0/1/2 one thread per ray with IEEE / two-step / one-step (default) slab
+ *                     division; 10..24 persistent warps with a global queue; 40..43 chunk-persistent warps
+ *   "bin_rays"        1 (default): counting sort of the ray queue by direction / origin cell before extend;
+ *                     "bin_y", "bin_t", "bin_p": the bin grid
+ *   "pipeline"        1 (default): generate + bin of launch k+1 on a second stream next to extend k
+ *   "overlap_extend"  1 (default): uvrt_trace alternates two extend streams / count buffers, so extend k+1 fills
+ *                     the SMs that the last wave of extend k leaves idle
+ *   "fetch_mode"      3 (default): rays, permutation, results bypass L1; 0 plain; 1/2 texture path; 4 evict_last
+ *                     nodes; 5 SM-affine chunks
+ *   "host_repack"     0 (default): uvrt_upload_scene repacks the scene on the device; 1: on the host cores
+ *   "stage_timing"    1: bracket every launch with CUDA events (uvrt_stage_time)
+ *   "simple_cfg", "hist_mode", "refill", "chunk", "blocks_per_sm", "generic_octant", "carveout": sweep knobs
+ *   read only: "scene_tame" (1 = every box coordinate is 0 or in [2^-77, 2^20]: fast slab division allowed) */
 int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value);
 int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value);
 /* Sum of event-timed durations and number of launches of a stage since the last
