@@ -710,6 +710,22 @@ static void par_copy(void* dst, const void* src, size_t bytes)
     }
 }
 
+// Host array -> pinned staging -> device in pieces, so that the DMA of one piece runs while the host
+// cores copy the next (the user's arrays are pageable; the staging copy is as slow as the DMA).
+static cudaError_t stage_and_copy(void* dDst, const void* hSrc, char* stage, size_t bytes, cudaStream_t st)
+{
+    // a room (a few MB) goes up in one piece -- the copy is spread over the host cores and takes as long as
+    // starting several DMAs would; large scenes in 32 MiB pieces
+    const size_t piece = bytes > (8u << 20) ? (32u << 20) : bytes;
+    for (size_t off = 0; off < bytes; off += piece) {
+        const size_t n = std::min(piece, bytes - off);
+        par_copy(stage + off, (const char*)hSrc + off, n);
+        cudaError_t e = cudaMemcpyAsync((char*)dDst + off, stage + off, n, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 // The repack on the device (uvrt_scene_prep.cuh): the reference's three arrays go up as they are.
 static int upload_scene_device(uvrt_ctx* ctx, const void* trisV, int nTris, const void* nodesV, int nNodes, const uint32_t* triIdx)
 {
@@ -759,14 +775,12 @@ static int upload_scene_device(uvrt_ctx* ctx, const void* trisV, int nTris, cons
     uint32_t *arrive = parent + (size_t)ctx->prepNodeCap, *subInner = arrive + (size_t)ctx->prepNodeCap,
              *subSlots = subInner + (size_t)ctx->prepNodeCap;
     // nodes + triIdx first: the tree walk needs nothing else and runs while the triangles are staged
-    par_copy(stage, nodesV, nodeBytes);
-    par_copy(stage + idxOff, triIdx, idxBytes);
-    phase("stage nodes+idx");
-    CK(cudaMemcpyAsync(ctx->dRawNodes, stage, nodeBytes, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->dRawIdx, stage + idxOff, idxBytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->dPrepQueue, 0xff, (size_t)nNodes * 8, st));
     CK(cudaMemsetAsync(parent, 0xff, (size_t)nNodes * 4, st));
     CK(cudaMemsetAsync(arrive, 0, (size_t)nNodes * 4, st));
+    CK(stage_and_copy(ctx->dRawNodes, nodesV, stage, nodeBytes, st));
+    CK(stage_and_copy(ctx->dRawIdx, triIdx, stage + idxOff, idxBytes, st));
+    phase("stage+copy nodes, idx");
     k_prep_init<<<1, 1, 0, st>>>(ctx->dPrepQueue, dSt, parent);
     const int blocks = (int)std::min<long long>(ctx->prepBlocks, ((long long)nNodes + 127) / 128);
     k_prep_walk<<<blocks, 128, 0, st>>>((const RawNode*)ctx->dRawNodes, (uint32_t)nNodes, ctx->dRawIdx, (uint32_t)nTris, kStack,
@@ -774,7 +788,6 @@ static int upload_scene_device(uvrt_ctx* ctx, const void* trisV, int nTris, cons
     CK(cudaMemcpyAsync(hSt, dSt, sizeof(Status), cudaMemcpyDeviceToHost, st));
     ctx->launches += 2;
     phase("enqueue copies+walk");
-    par_copy(stage + vertOff, trisV, vertBytes);
     // the triangles travel on the second stream, next to the walk, into a spare buffer: the previous
     // scene stays intact until the new tree has been validated
     if ((size_t)nTris > ctx->vertsSpareCap) {
@@ -783,7 +796,7 @@ static int upload_scene_device(uvrt_ctx* ctx, const void* trisV, int nTris, cons
         ctx->vertsSpareCap = (size_t)nTris;
     }
     if (!ctx->vertsEv) CK(cudaEventCreateWithFlags(&ctx->vertsEv, cudaEventDisableTiming));
-    CK(cudaMemcpyAsync(ctx->dVertsSpare, stage + vertOff, vertBytes, cudaMemcpyHostToDevice, ctx->genStream));
+    CK(stage_and_copy(ctx->dVertsSpare, trisV, stage + vertOff, vertBytes, ctx->genStream));
     CK(cudaEventRecord(ctx->vertsEv, ctx->genStream));
     phase("stage triangles");
     CK(cudaStreamSynchronize(st));
