@@ -16,6 +16,7 @@
 #include <cstring>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace uvrt;
@@ -699,11 +700,20 @@ static int ensure_stage(uvrt_ctx* ctx, size_t total)
 }
 
 // memcpy spread over the host cores (the staging copy of a 1 GB scene is otherwise the slowest step)
+// Threads: the host's cores divided by the ranks sharing it (uvrt_comm_init tells how many there are;
+// launchers such as torchrun set OMP_NUM_THREADS=1, which would leave one core per rank copying).
+static int g_copyThreads = 0;
 static void par_copy(void* dst, const void* src, size_t bytes)
 {
-    const size_t chunk = 1u << 20;
+    const size_t chunk = 256u << 10;
     const long long nChunks = (long long)((bytes + chunk - 1) / chunk);
-#pragma omp parallel for schedule(static) if (nChunks > 2)
+    int threads = g_copyThreads;
+    if (threads <= 0) {
+        threads = (int)std::thread::hardware_concurrency();
+        if (const char* e = getenv("OMP_NUM_THREADS")) { int v = atoi(e); if (v >= 1) threads = v; }
+        threads = std::max(1, std::min(threads, 16));
+    }
+#pragma omp parallel for schedule(static) num_threads(threads) if (nChunks > 2)
     for (long long c = 0; c < nChunks; c++) {
         const size_t off = (size_t)c * chunk;
         memcpy((char*)dst + off, (const char*)src + off, std::min(chunk, bytes - off));
@@ -1487,6 +1497,7 @@ int uvrt_comm_init(uvrt_ctx* ctx, const void* id128, int rank, int nRanks)
     if (r != kNcclSuccess) return fail(ctx, UVRT_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
     ctx->rank = rank;
     ctx->nRanks = nRanks;
+    if (nRanks > 1) g_copyThreads = std::max(1, std::min(16, (int)std::thread::hardware_concurrency() / nRanks));
     return UVRT_OK;
 }
 
