@@ -141,6 +141,7 @@ struct uvrt_ctx {
     cudaEvent_t extDone[2] = {nullptr, nullptr}, accDone[2] = {nullptr, nullptr}, forkEv = nullptr;
     bool extUsed[2] = {false, false}, accUsed[2] = {false, false};
     bool mainForeign = true;             // something other than an overlapped trace touched the main stream
+    bool countsDirty = false;            // UVRT_BUF_COUNTS holds counts no accumulate has consumed yet
     int* dCountsAlt = nullptr;           // count buffer of slot 1
     cudaStream_t xStream = nullptr;      // stream / count buffer of the extend being launched
     int* xCounts = nullptr;
@@ -1169,6 +1170,7 @@ int uvrt_reset(uvrt_ctx* ctx, int resetColor)
     }
     CK(cudaMemsetAsync(ctx->dCountsAlt, 0, (size_t)ctx->nTris * 4, ctx->stream));
     ctx->launches++;
+    ctx->countsDirty = false;
     CK_LAUNCH("reset");
     return UVRT_OK;
 }
@@ -1228,6 +1230,7 @@ int uvrt_extend(uvrt_ctx* ctx, int64_t nRays)
     const uint32_t* perm = nullptr;
     ctx->xStream = ctx->stream;
     ctx->xCounts = ctx->dCounts;
+    ctx->countsDirty = true;
     // a few thousand rays are not worth the extra launches
     if (ctx->binRays && nRays >= kMinRaysForBinning) {
         if (ctx->rs().permRays != nRays) {          // not already done on the generate stream
@@ -1259,6 +1262,7 @@ int uvrt_accumulate(uvrt_ctx* ctx, float duration)
         k_accumulate<<<grid_for(ctx->nTris, 256), 256, 0, ctx->stream>>>(ctx->dSum, ctx->dMax, ctx->dCounts, duration, ctx->nTris);
     }
     ctx->launches++;
+    ctx->countsDirty = false;
     CK_LAUNCH("accumulate");
     return UVRT_OK;
 }
@@ -1304,7 +1308,9 @@ int uvrt_trace(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, f
     const bool foreign = ctx->mainForeign;
     const int variant = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
     const bool sharedQueue = variant >= 10 && variant < 25;   // variant B's global queue head is one per context
-    if (!ctx->pipeline || !ctx->overlapExtend || nRays <= 0 || sharedQueue) {
+    // counts left behind by uvrt_extend / uvrt_trace_counts belong to this launch's accumulate as well: they sit
+    // in the primary buffer, so this launch must use it too
+    if (!ctx->pipeline || !ctx->overlapExtend || nRays <= 0 || sharedQueue || ctx->countsDirty) {
         int rc = uvrt_trace_counts(ctx, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
         if (rc) return rc;
         return uvrt_accumulate(ctx, duration);
@@ -1458,6 +1464,7 @@ int uvrt_write(uvrt_ctx* ctx, uvrt_buffer what, const void* src, size_t bytes)
     if (!src || bytes > cap) return fail(ctx, UVRT_ERR_INVALID, "write: %zu bytes offered, buffer %d holds %zu", bytes, (int)what, cap);
     if (bytes) CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (what == UVRT_BUF_COUNTS) ctx->countsDirty = true;
     return UVRT_OK;
 }
 

@@ -702,3 +702,26 @@ def test_headless_driver_cli(uv, golden, tmp_path):
     assert np.fromfile(two, dtype=np.float32).tobytes() == np.fromfile(resumed, dtype=np.float32).tobytes()
     bad = subprocess.run(base[:3] + ["--room", "no_such_room"], capture_output=True, text=True, timeout=60)
     assert bad.returncode == 1 and "cannot load room" in bad.stderr
+
+
+def test_stage_calls_and_trace_share_the_count_buffer(uv, ctx, room):
+    """generate + extend through the stage API leave their counts for the next accumulate, and uvrt_trace's
+    accumulate must see them even though uvrt_trace normally alternates between two count buffers
+    (reference order: extend, extend, accumulate adds both launches' photons with the second duration)."""
+    lp = lange_pos0(room[3])
+    P = 200_000
+    for start_slot in (0, 1):
+        ctx.reset(True)
+        if start_slot:
+            ctx.trace(lp, 1.0, 1.0, 0, 70_000, 5)            # moves the context to the other ray slot
+            ctx.reset(True)
+        ctx.trace_counts(lp, 1.0, 0, P, 11)                   # counts only
+        first = ctx.read(uv.BUF.COUNTS).astype(np.float64)
+        ctx.trace(lp, 1.0, 2.5, 0, P, 12)                     # extend + accumulate
+        total = ctx.read(uv.BUF.SUM)
+        assert not ctx.read(uv.BUF.COUNTS).any()              # accumulate zeroed what it consumed
+        ctx.reset(True)
+        ctx.trace_counts(lp, 1.0, 0, P, 12)
+        second = ctx.read(uv.BUF.COUNTS).astype(np.float64)
+        assert np.array_equal(total, (first + second) * 2.5)
+    ctx.reset(True)
