@@ -361,7 +361,7 @@ void launch_simple(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 }
 
 template <int FETCH>
-void launch_simple_tex(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
+void launch_simple_fetch(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
     if (ctx->carveout >= 0) {
         cudaFuncSetAttribute(k_extend_simple<DIV_MARKSTEIN1, kStack, 128, 12, FETCH>, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->carveout);
@@ -484,11 +484,11 @@ int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     int v = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
     if (v == 0) launch_simple<DIV_IEEE>(ctx, nRays, perm);
     else if (v == 1) launch_simple<DIV_MARKSTEIN2>(ctx, nRays, perm);
-    else if (v == 2 && ctx->fetchMode == 1 && ctx->pairsTex) launch_simple_tex<1>(ctx, nRays, perm);
-    else if (v == 2 && ctx->fetchMode == 2 && ctx->pairsTex) launch_simple_tex<2>(ctx, nRays, perm);
-    else if (v == 2 && ctx->fetchMode == 3 && ctx->simpleCfg == 1) launch_simple_tex<3>(ctx, nRays, perm);
-    else if (v == 2 && ctx->fetchMode == 4) launch_simple_tex<4>(ctx, nRays, perm);
-    else if (v == 2 && ctx->fetchMode == 5 && perm) launch_simple_tex<5>(ctx, nRays, perm);
+    else if (v == 2 && ctx->fetchMode == 1 && ctx->pairsTex) launch_simple_fetch<1>(ctx, nRays, perm);
+    else if (v == 2 && ctx->fetchMode == 2 && ctx->pairsTex) launch_simple_fetch<2>(ctx, nRays, perm);
+    else if (v == 2 && ctx->fetchMode == 3 && ctx->simpleCfg == 1) launch_simple_fetch<3>(ctx, nRays, perm);
+    else if (v == 2 && ctx->fetchMode == 4) launch_simple_fetch<4>(ctx, nRays, perm);
+    else if (v == 2 && ctx->fetchMode == 5 && perm) launch_simple_fetch<5>(ctx, nRays, perm);
     else if (v == 2) launch_simple<DIV_MARKSTEIN1>(ctx, nRays, perm);
     else if (v >= 40 && v < 44) {
         // chunk-persistent warps (k_extend_chunk): K = {1, 2, 4, 8}[v - 40]; "refill", "chunk" options
