@@ -74,8 +74,10 @@ __device__ __forceinline__ float half_area(const float* lo, const float* hi)
 
 __device__ __forceinline__ int bin_of(float c, float lo, float scale)
 {
-    int b = (int)fm(fs(c, lo), scale);
-    return b < kBins - 1 ? b : kBins - 1;
+    // (the clamps only matter for NaN / infinite coordinates; for finite input the product lies in [0, 8])
+    const float x = fm(fs(c, lo), scale);
+    if (!(x >= 0.0f)) return 0;
+    return x >= (float)(kBins - 1) ? kBins - 1 : (int)x;
 }
 
 // centroid = (v0 + v1 + v2) * 0.3333f (bvh.cpp:23); also initialises the identity index array

@@ -36,6 +36,14 @@ inline void grow(float* lo, float* hi, const float3_strict& p)
     lo[1] = p.y < lo[1] ? p.y : lo[1]; hi[1] = p.y > hi[1] ? p.y : hi[1];
     lo[2] = p.z < lo[2] ? p.z : lo[2]; hi[2] = p.z > hi[2] ? p.z : hi[2];
 }
+// bin = min(BINS - 1, (int)((c - lo) * scale)) (bvh.cpp:117, 58).  For finite input the product lies in [0, 8];
+// the lower clamp only matters for NaN / infinite coordinates, where the reference indexes out of bounds.
+inline int BinOf(float c, float lo, float scale)
+{
+    const float x = (c - lo) * scale;
+    if (!(x >= 0.0f)) return 0;
+    return x >= (float)(BINS - 1) ? BINS - 1 : (int)x;
+}
 inline void reset(float* lo, float* hi)
 {
     lo[0] = lo[1] = lo[2] = 1e30f;
@@ -104,7 +112,7 @@ float BVH::BestSplit(const BVHNode& node, const Bounds3& cb, int& axis, int& pla
         for (int b = 0; b < BINS; b++) { reset(binLo[b], binHi[b]); count[b] = 0; }
         for (uint i = 0; i < node.triCount; i++) {
             const Tri& t = mesh->triangles[triIdx[node.leftFirst + i]];
-            int b = std::min(BINS - 1, (int)((t.centroid[a] - lo) * scale));
+            int b = BinOf(t.centroid[a], lo, scale);
             count[b]++;
             grow(binLo[b], binHi[b], t.vertex0);
             grow(binLo[b], binHi[b], t.vertex1);
@@ -151,7 +159,7 @@ void BVH::Split(uint nodeIdx, int level, uint& nextFree, Bounds3 cb, std::vector
     const float lo = cb.lo[axis];
     const float scale = BINS / (cb.hi[axis] - lo);
     while (i <= j) {
-        int b = std::min(BINS - 1, (int)((mesh->triangles[triIdx[i]].centroid[axis] - lo) * scale));
+        int b = BinOf(mesh->triangles[triIdx[i]].centroid[axis], lo, scale);
         if (b < plane) i++;
         else std::swap(triIdx[i], triIdx[j--]);
     }

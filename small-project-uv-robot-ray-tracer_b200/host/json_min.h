@@ -30,7 +30,11 @@ struct Value {
         return (kind == Array && i < arr.size()) ? arr[i] : none;
     }
     size_t size() const { return kind == Array ? arr.size() : kind == Object ? obj.size() : 0; }
-    long long as_int(long long dflt = 0) const { return kind == Number ? (long long)num : dflt; }
+    // out-of-range and non-finite numbers (1e99, NaN) map to the default instead of an undefined conversion
+    long long as_int(long long dflt = 0) const
+    {
+        return (kind == Number && num > -9.0e18 && num < 9.0e18) ? (long long)num : dflt;
+    }
     bool is_number() const { return kind == Number; }
 };
 

@@ -70,12 +70,20 @@ bool resolve(const uvrt_json::Value& js, const unsigned char* bin, size_t binLen
     const uvrt_json::Value& bv = js["bufferViews"][(size_t)acc["bufferView"].as_int(-1)];
     if (bv.kind != uvrt_json::Value::Object) { err = "bufferView missing"; return false; }
     if (bv["buffer"].as_int(0) != 0) { err = "only the embedded GLB buffer is supported"; return false; }
-    size_t off = (size_t)bv["byteOffset"].as_int(0) + (size_t)acc["byteOffset"].as_int(0);
-    out.count = (size_t)acc["count"].as_int(0);
+    // every number below comes from the file: negative, fractional-huge or wrapping values must not get through
+    const long long o1 = bv["byteOffset"].as_int(0), o2 = acc["byteOffset"].as_int(0);
+    const long long cnt = acc["count"].as_int(0), strideIn = bv["byteStride"].as_int(0);
+    if (o1 < 0 || o2 < 0 || cnt < 0 || strideIn < 0 || (unsigned long long)o1 > binLen || (unsigned long long)o2 > binLen ||
+        (unsigned long long)cnt > binLen || (unsigned long long)strideIn > binLen) { err = "accessor exceeds the BIN chunk"; return false; }
+    size_t off = (size_t)o1 + (size_t)o2;
+    out.count = (size_t)cnt;
     out.componentType = (int)acc["componentType"].as_int(0);
-    out.stride = (size_t)bv["byteStride"].as_int(0);
+    out.stride = (size_t)strideIn;
     if (out.stride == 0) out.stride = elemBytes;
-    if (out.count && off + (out.count - 1) * out.stride + elemBytes > binLen) { err = "accessor exceeds the BIN chunk"; return false; }
+    if (out.count && (off > binLen || (out.count - 1) > (binLen - off) / out.stride || off + (out.count - 1) * out.stride + elemBytes > binLen)) {
+        err = "accessor exceeds the BIN chunk";
+        return false;
+    }
     out.data = bin + off;
     return true;
 }
@@ -83,6 +91,18 @@ bool resolve(const uvrt_json::Value& js, const unsigned char* bin, size_t binLen
 } // namespace
 
 void Mesh::LoadMesh()
+{
+    try {
+        LoadMeshImpl();
+    } catch (const std::exception& e) {
+        // out-of-memory or a length the file lied about: a load failure like any other (the reference would crash)
+        Release();
+        lastError = std::string("rooms/") + modelFile + ".glb: " + e.what();
+        printf("Failed to parse glTF: %s\n", lastError.c_str());
+    }
+}
+
+void Mesh::LoadMeshImpl()
 {
     std::cout << "Loading mesh " << std::endl;
     Release();
@@ -246,6 +266,9 @@ void Mesh::LoadMesh()
 
     const size_t nTri = outPos.size() / 9;
     if (nTri == 0) return bail("no triangles");
+    // NaN / infinite coordinates would index out of the builder's bins (the reference does not check either)
+    for (float v : outPos)
+        if (!std::isfinite(v)) return bail("a vertex coordinate is not finite");
     if (nTri > 0x3fffffffu) return bail("too many triangles");
     void* mem = nullptr;
     if (posix_memalign(&mem, 64, sizeof(Tri) * nTri) != 0) return bail("out of memory");
@@ -278,7 +301,13 @@ void Mesh::LoadMesh()
 void Mesh::SetTriangles(const Tri* tris, int n, bool buildBvh)
 {
     Release();
+    lastError.clear();
     if (n <= 0) return;
+    for (int t = 0; t < n; t++) {
+        const float* v = reinterpret_cast<const float*>(&tris[t]);
+        for (int k = 0; k < 12; k++)
+            if ((k & 3) != 3 && !std::isfinite(v[k])) { lastError = "SetTriangles: a vertex coordinate is not finite"; return; }
+    }
     void* mem = nullptr;
     if (posix_memalign(&mem, 64, sizeof(Tri) * (size_t)n) != 0) return;
     memcpy(mem, tris, sizeof(Tri) * (size_t)n);

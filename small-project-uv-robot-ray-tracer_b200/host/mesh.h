@@ -53,6 +53,7 @@ public:
 
 private:
     void Release();
+    void LoadMeshImpl();
 };
 
 } // namespace Tmpl8

@@ -74,7 +74,8 @@ int uvrt_sim_set_triangles(uvrt_sim* s, const void* tris, int n)
 {
     if (!s || !tris || n <= 0) return UVRT_ERR_INVALID;
     s->mesh.SetTriangles((const Tri*)tris, n, true);
-    if (!s->mesh.loadedMesh) return sim_fail(s, UVRT_ERR_NO_MEMORY, "SetTriangles failed");
+    if (!s->mesh.loadedMesh)
+        return s->mesh.lastError.empty() ? sim_fail(s, UVRT_ERR_NO_MEMORY, "SetTriangles failed") : sim_fail(s, UVRT_ERR_INVALID, s->mesh.lastError);
     return UVRT_OK;
 }
 
@@ -325,6 +326,7 @@ int uvrt_host_build_bvh(void* tris, int n, void* nodesOut, int nodeCapacity, uns
     if (!tris || n <= 0 || !nodesOut || !triIdxOut) return UVRT_ERR_INVALID;
     Mesh m;
     m.SetTriangles((const Tri*)tris, n, true);
+    if (!m.loadedMesh && !m.lastError.empty()) return UVRT_ERR_INVALID;   // non-finite coordinates
     if (!m.bvh || !m.bvh->bvhNode) return UVRT_ERR_NO_MEMORY;
     if ((int)m.bvh->nodesUsed > nodeCapacity) return UVRT_ERR_INVALID;
     memcpy(nodesOut, m.bvh->bvhNode, sizeof(BVHNode) * (size_t)m.bvh->nodesUsed);

@@ -328,3 +328,77 @@ def test_whole_scene_loader_multi_primitive_and_transforms(uv, tmp_path):
     sim.load_mesh("room")
     assert sim.mesh_data()[0].tobytes() == a.tobytes()
     uv.Sim(asset_root=T.DATA)  # restore the asset root for later tests
+
+
+def test_loaders_survive_corrupt_files(uv, tmp_path):
+    """T7 (fault): byte flips, truncations, absurd numbers, cyclic node graphs and non-finite transforms in a
+    .glb, and byte flips / truncations in a route file, end in an error code or in a loaded mesh -- never in a
+    crash (the reference prints and carries on, or indexes out of bounds)."""
+    import json
+    import random
+    rng = random.Random(3)
+    os.makedirs(tmp_path / "rooms")
+    os.makedirs(tmp_path / "positions")
+    p0 = np.random.default_rng(1).uniform(-1, 1, (6, 3)).astype("<f4")
+    i0 = np.array([0, 1, 2, 3, 4, 5, 0, 2, 4], dtype="<u2")
+    blob = p0.tobytes() + i0.tobytes() + b"\0\0"
+    js = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}],
+          "nodes": [{"mesh": 0, "children": [1]}, {"mesh": 0, "translation": [1, 2, 3]}],
+          "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}],
+          "buffers": [{"byteLength": len(blob)}],
+          "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 72}, {"buffer": 0, "byteOffset": 72, "byteLength": 18}],
+          "accessors": [{"bufferView": 0, "componentType": 5126, "count": 6, "type": "VEC3"},
+                        {"bufferView": 1, "componentType": 5123, "count": 9, "type": "SCALAR"}]}
+    _write_glb(tmp_path / "rooms" / "base.glb", js, blob)
+    base = open(tmp_path / "rooms" / "base.glb", "rb").read()
+    sim = uv.Sim(asset_root=str(tmp_path))
+    loaded = rejected = 0
+    for whole in (False, True):
+        sim.set_whole_scene(whole)
+        for case in range(400):
+            kind = case % 4
+            if kind == 0:
+                b = bytearray(base)
+                for _ in range(rng.randint(1, 4)):
+                    b[rng.randrange(len(b))] = rng.randrange(256)
+            elif kind == 1:
+                b = base[: rng.randrange(len(base))]
+            else:
+                j = json.loads(json.dumps(js))
+                if kind == 2:
+                    tgt = rng.choice(["accessors", "bufferViews", "nodes", "scenes", "meshes"])
+                    s = json.dumps(j[tgt])
+                    digits = [k for k, ch in enumerate(s) if ch.isdigit()]
+                    k = rng.choice(digits)
+                    s = s[:k] + rng.choice(["9999999", "-1", "0", "4294967295", "1e99", "7"]) + s[k + 1:]
+                    try:
+                        j[tgt] = json.loads(s)
+                    except ValueError:
+                        continue
+                else:
+                    j["nodes"][1]["children"] = [rng.choice([0, 1, 5, -3])]       # cycles, missing nodes
+                _write_glb(tmp_path / "rooms" / "m.glb", j, blob)
+                b = open(tmp_path / "rooms" / "m.glb", "rb").read()
+            (tmp_path / "rooms" / "f.glb").write_bytes(bytes(b))
+            try:
+                sim.load_mesh("f")
+                loaded += 1
+            except uv.UvrtError:
+                rejected += 1
+    assert loaded > 50 and rejected > 200
+    bad = np.zeros((3, 16), dtype=np.float32)
+    bad[1, 5] = np.inf
+    with pytest.raises(uv.UvrtError):
+        sim.set_triangles(bad)
+    route = open(os.path.join(T.DATA, "positions", "route.xml"), "rb").read()
+    for case in range(400):
+        b = bytearray(route)
+        if case % 2:
+            b = b[: rng.randrange(len(b))]
+        else:
+            for _ in range(rng.randint(1, 6)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        (tmp_path / "positions" / "f.xml").write_bytes(bytes(b))
+        sim.load_route("f")                      # never raises: a broken file leaves the settings alone
+        assert sim.params.photonCount is not None
+    uv.Sim(asset_root=T.DATA)  # restore the asset root for later tests
