@@ -107,3 +107,55 @@ def test_build_repack_extend_on_awkward_meshes(uv):
     assert traced > 100
     ctx_d.close()
     ctx_h.close()
+
+
+def test_upload_of_corrupted_trees_agrees_with_host_validation(uv):
+    """Random damage to the node array / triIdx of the room (wild child indices, cycles, leaves that run off the
+    end, inner nodes turned into leaves and back): the device-side tree walk must reach the same verdict as the
+    host-side validation -- the same error class, or the same repacked scene -- and must always return."""
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_mesh("testroomopt")
+    tris, nodes, tri_idx = (a.copy() for a in sim.mesh_data())
+    rng = np.random.default_rng(5)
+    ctx_d, ctx_h = uv.Context(0), uv.Context(0)
+    ctx_h.set_option("host_repack", 1)
+    n_nodes, n_tris = len(nodes), tris.shape[0]
+    verdicts = {"ok": 0, "error": 0}
+    for case in range(120):
+        nd, ix = nodes.copy(), tri_idx.copy()
+        for _ in range(int(rng.integers(1, 4))):
+            k = int(rng.integers(0, n_nodes))
+            kind = int(rng.integers(0, 6))
+            if kind == 0:
+                nd[k]["leftFirst"] = rng.integers(0, 2 ** 32, dtype=np.uint64).astype(np.uint32)
+            elif kind == 1:
+                nd[k]["leftFirst"] = rng.integers(0, n_nodes)                 # likely a second parent or a cycle
+            elif kind == 2:
+                nd[k]["triCount"] = rng.integers(0, 5)
+            elif kind == 3:
+                nd[k]["triCount"] = rng.integers(n_tris, 2 ** 32, dtype=np.uint64).astype(np.uint32)
+            elif kind == 4:
+                ix[int(rng.integers(0, n_tris))] = rng.integers(n_tris, 2 ** 32, dtype=np.uint64).astype(np.uint32)
+            else:
+                nd[k]["leftFirst"], nd[k]["triCount"] = 0, 0                  # a zeroed slot: children 0 and 1
+        out = []
+        for ctx in (ctx_h, ctx_d):
+            try:
+                ctx.upload_scene(tris, nd, ix)
+                out.append(("ok", ctx.scene_info(), ctx.read(uv.BUF.PAIRS).tobytes(), ctx.read(uv.BUF.WTRIS).tobytes()))
+            except uv.UvrtError as e:
+                out.append(("error", e.code))
+        assert out[0][0] == out[1][0], f"case {case}: host says {out[0][:2]}, device says {out[1][:2]}"
+        if out[0][0] == "ok":
+            assert out[0] == out[1], f"case {case}: repacked scenes differ"
+        else:
+            assert out[0][1] == out[1][1] == -1
+        verdicts[out[0][0]] += 1
+    assert verdicts["error"] > 20
+    # and both contexts still work
+    for ctx in (ctx_h, ctx_d):
+        ctx.upload_scene(tris, nodes, tri_idx)
+        assert ctx.scene_info()["inner"] == 44708
+    ctx_d.close()
+    ctx_h.close()
+    sim.close()
