@@ -312,6 +312,13 @@ int check_buffer(uvrt_ctx* ctx, uvrt_buffer what, void** ptr, size_t* bytes)
     return fail(ctx, UVRT_ERR_INVALID, "unknown buffer id %d", (int)what);
 }
 
+constexpr long long kMinRaysForBinning = 65536;   // a few thousand rays are not worth the extra launches
+constexpr int kMinPairsForBinning = 32;           // nor is a tree of a few nodes (CalibratePower's two triangles)
+inline bool wants_binning(const uvrt_ctx* ctx, long long nRays)
+{
+    return ctx->binRays && nRays >= kMinRaysForBinning && ctx->nPairs >= kMinPairsForBinning;
+}
+
 inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
 // ---- extend dispatch ---------------------------------------------------------------------------
@@ -321,7 +328,6 @@ inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block 
 //   2  simple / Markstein one-step
 //   10 + 3*k + d  persistent, K = {1, 2, 4, 8, inf}[k], d = {IEEE, M2, M1}
 constexpr int kStack = 64;
-constexpr long long kMinRaysForBinning = 65536;
 constexpr int kDefaultVariant = 2;   // one thread per ray, one-step shared-reciprocal division (proven exact)
 
 template <int DIV, int THREADS, int MINB>
@@ -1230,7 +1236,7 @@ static int generate_on(uvrt_ctx* ctx, cudaStream_t stream, float lx, float ly, f
         S.countedRays = -1;
     }
     if (nRays == 0) return UVRT_OK;
-    if (ctx->binRays && nRays >= kMinRaysForBinning) {
+    if (wants_binning(ctx, nRays)) {
         BinDims d;
         rc = bin_prepare(ctx, nRays, &d);
         if (rc) return rc;
@@ -1267,7 +1273,7 @@ int uvrt_extend(uvrt_ctx* ctx, int64_t nRays)
     ctx->xCounts = ctx->dCounts;
     ctx->countsDirty = true;
     // a few thousand rays are not worth the extra launches
-    if (ctx->binRays && nRays >= kMinRaysForBinning) {
+    if (wants_binning(ctx, nRays)) {
         if (ctx->rs().permRays != nRays) {          // not already done on the generate stream
             rc = bin_finish(ctx, nRays, ctx->stream);
             if (rc) return rc;
@@ -1319,7 +1325,7 @@ int uvrt_trace_counts(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLe
     if (S.inFlight) CK(cudaStreamWaitEvent(ctx->genStream, S.freeEv, 0));   // the extend that last read this slot
     int rc = generate_on(ctx, ctx->genStream, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
     if (rc) return rc;
-    if (ctx->binRays && nRays >= kMinRaysForBinning && S.countedRays == nRays) {
+    if (wants_binning(ctx, nRays) && S.countedRays == nRays) {
         // scan + scatter of the ray binning also run ahead, next to the previous launch's extend
         rc = bin_finish(ctx, nRays, ctx->genStream);
         if (rc) return rc;
@@ -1375,7 +1381,7 @@ int uvrt_trace(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, f
     int rc = generate_on(ctx, ctx->genStream, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
     if (rc) return rc;
     const uint32_t* perm = nullptr;
-    if (ctx->binRays && nRays >= kMinRaysForBinning) {
+    if (wants_binning(ctx, nRays)) {
         rc = bin_finish(ctx, nRays, ctx->genStream);
         if (rc) return rc;
         CK_LAUNCH("bin");
