@@ -1,0 +1,117 @@
+"""BASELINE.json config 3: high-sample dose convergence run (1e9 rays) on 1/2/4/8 GPUs.
+
+The room of that config (C046_1_opt.glb) is not in the reference checkout (.MISSING_LARGE_BLOBS), so this runs
+on rooms/testroomopt.glb -- the SUBSTITUTE is stated in the output.  30 iterations of lange_route.xml
+(12 positions x 2,796,202 rays) = 1,006,632,720 rays.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/convergence_run.py [--iterations 30]
+
+Part 1 (timed): RayTracer run with the launches dealt over the ranks, one NCCL all-reduce, computeDosage,
+dose map read back on rank 0: wall clock, max over ranks.
+Part 2 (not timed): the same run again, stopping after 1, 2, 5, 10, 20 and 30 iterations to sum the ranks'
+photon maps on the side (the device buffers are left alone) and report how far the dose map still is from the
+30-iteration one: median and 95th percentile of |dose_k - dose_30| / dose_30 over the triangles that receive at
+least the minimal dose (minimale_dosis of the route file).
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+uv = importlib.import_module("small-project-uv-robot-ray-tracer_b200")
+B = importlib.import_module("small-project-uv-robot-ray-tracer_b200.binding")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iterations", type=int, default=30)
+    ap.add_argument("--route", default="lange_route")
+    args = ap.parse_args()
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sim = uv.Sim(asset_root=os.path.join(ROOT, "data"), device=local)
+    sim.load_mesh("testroomopt")
+    sim.init(args.route)
+    ctx = sim.ctx
+    if dist is not None:
+        import torch
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(B.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        ctx.comm_init(bytes(idt.cpu().tolist()), rank, world)
+        sim.set_shard(rank, world)
+    sim.set_params(maxIterations=args.iterations)
+    p = sim.params
+    rays = args.iterations * len(sim.positions) * int(p.photonsPerLight)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sim.run()                                  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    dose_final = sim.run()
+    wall = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+
+    # ---- convergence (not timed) ----
+    tris = sim.mesh_data()[0]
+    v0, v1, v2 = (tris[:, 0:3].astype(np.float64), tris[:, 4:7].astype(np.float64), tris[:, 8:11].astype(np.float64))
+    area = 0.5 * np.linalg.norm(np.cross(v0 - v1, v0 - v2), axis=1)
+    stops = [k for k in (1, 2, 5, 10, 20, args.iterations) if k <= args.iterations]
+    maps = {}
+    sim.reset_dosage_map()
+    for it in range(1, args.iterations + 1):
+        sim.tick()
+        if it in stops:
+            local_sum = ctx.read(uv.BUF.SUM)
+            if dist is not None:
+                import torch
+                t = torch.from_numpy(local_sum).cuda()
+                dist.all_reduce(t)
+                local_sum = t.cpu().numpy()
+            per_light = it * int(p.photonsPerLight)           # photonMapSize / L after `it` iterations
+            with np.errstate(divide="ignore", invalid="ignore"):
+                maps[it] = np.float64(p.lightIntensity) * 0.1 * local_sum / (area * per_light)
+    if rank == 0:
+        ref = maps[stops[-1]]
+        lit = np.isfinite(ref) & (ref >= float(p.minDosage))
+        conv = []
+        for k in stops[:-1]:
+            rel = np.abs(maps[k][lit] - ref[lit]) / ref[lit]
+            conv.append({"iterations": k, "rays": k * len(sim.positions) * int(p.photonsPerLight),
+                         "median_rel_diff": round(float(np.median(rel)), 5), "p95_rel_diff": round(float(np.percentile(rel, 95)), 5)})
+        agree = float(np.max(np.abs(dose_final[lit] - ref[lit]) / ref[lit]))     # f32 device dose against the f64 host formula
+        print(json.dumps({"config": "high-sample dose convergence run", "room": "testroomopt.glb (SUBSTITUTE for the absent C046_1_opt.glb)",
+                          "route": args.route + ".xml", "n_gpus": world, "iterations": args.iterations, "rays": rays,
+                          "wall_ms": round(wall * 1e3, 2), "mrays_s": round(rays / wall / 1e6, 1),
+                          "triangles_above_min_dose": int(lit.sum()), "triangles": int(len(ref)),
+                          "convergence_vs_final": conv, "device_dose_vs_host_formula_max_rel": agree}), flush=True)
+    sim.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
