@@ -77,8 +77,11 @@ def main():
 
     # ---- convergence (not timed) ----
     tris = sim.mesh_data()[0]
-    v0, v1, v2 = (tris[:, 0:3].astype(np.float64), tris[:, 4:7].astype(np.float64), tris[:, 8:11].astype(np.float64))
-    area = 0.5 * np.linalg.norm(np.cross(v0 - v1, v0 - v2), axis=1)
+    # area as shade.cl:29-31 forms it: fp32 edges, fp32 cross product and length (for sliver triangles this differs
+    # from the exact area by tens of percent -- it is the reference's arithmetic, and the device's)
+    v0, v1, v2 = tris[:, 0:3], tris[:, 4:7], tris[:, 8:11]
+    cr = np.cross(v0 - v1, v0 - v2).astype(np.float32)
+    area = (np.sqrt((cr[:, 0] * cr[:, 0] + cr[:, 1] * cr[:, 1] + cr[:, 2] * cr[:, 2]).astype(np.float32)) / np.float32(2)).astype(np.float64)
     stops = [k for k in (1, 2, 5, 10, 20, args.iterations) if k <= args.iterations]
     maps = {}
     sim.reset_dosage_map()
@@ -94,6 +97,11 @@ def main():
             per_light = it * int(p.photonsPerLight)           # photonMapSize / L after `it` iterations
             with np.errstate(divide="ignore", invalid="ignore"):
                 maps[it] = np.float64(p.lightIntensity) * 0.1 * local_sum / (area * per_light)
+    # the device's own dose map of this very run (same rays), for a cross-check of the host-side formula
+    if world > 1:
+        sim.reduce()
+    sim.shade()
+    dose_final = sim.read_dose()
     if rank == 0:
         ref = maps[stops[-1]]
         lit = np.isfinite(ref) & (ref >= float(p.minDosage))
