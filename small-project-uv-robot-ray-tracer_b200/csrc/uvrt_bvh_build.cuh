@@ -317,7 +317,13 @@ struct BlockBins {
             const int b = a * kBins + bin_of(c[a], nd.cmin[a], scale[a]);
             atomicAdd(&cnt[b], 1u);
 #pragma unroll
-            for (int k = 0; k < 3; k++) { atomicMin(&lo[b * 3 + k], enc(tlo[k])); atomicMax(&hi[b * 3 + k], enc(thi[k])); }
+            for (int k = 0; k < 3; k++) {
+                // the bounds are monotone, so a plain look first saves most of the atomics (a stale value only
+                // costs an atomic that changes nothing): after the first few triangles a bin's box rarely grows
+                const uint32_t el = enc(tlo[k]), eh = enc(thi[k]);
+                if (el < *(volatile uint32_t*)&lo[b * 3 + k]) atomicMin(&lo[b * 3 + k], el);
+                if (eh > *(volatile uint32_t*)&hi[b * 3 + k]) atomicMax(&hi[b * 3 + k], eh);
+            }
         }
     }
 };
