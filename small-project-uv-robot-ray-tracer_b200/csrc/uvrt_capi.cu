@@ -606,6 +606,11 @@ void uvrt_destroy(uvrt_ctx* ctx)
         if (ctx->extDone[k]) cudaEventDestroy(ctx->extDone[k]);
         if (ctx->accDone[k]) cudaEventDestroy(ctx->accDone[k]);
     }
+    if (ctx->poolTuned) {
+        // hand the memory that uvrt_build_bvh kept in the device's allocation pool back to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     if (ctx->forkEv) cudaEventDestroy(ctx->forkEv);
     if (ctx->accStream) { cudaStreamSynchronize(ctx->accStream); cudaStreamDestroy(ctx->accStream); }
     if (ctx->dCountsAlt) cudaFree(ctx->dCountsAlt);
