@@ -81,7 +81,9 @@ int uvrt_device_info(uvrt_ctx* ctx, char* dst, size_t bytes, int* smCount, int* 
  * the number of valid 32-B slots at `nodes` (node 0 = root, node 1 unused, bvh.cpp:16); every
  * node reachable from the root must lie inside it (the reference uploads 2N, which truncates
  * its own tree -- SURVEY App. B-3 -- and is rejected here with UVRT_ERR_INVALID).
- * (Re)allocates and zeroes the per-triangle buffers when nTris changes. */
+ * The arrays go up as they are; the tree is validated and repacked on the device.  A rejected upload
+ * leaves the previously uploaded scene usable.  (Re)allocates and zeroes the per-triangle buffers when
+ * nTris changes.  Synchronises. */
 int uvrt_upload_scene(uvrt_ctx* ctx, const void* tris, int nTris, const void* nodes, int nNodes,
                       const uint32_t* triIdx);
 
@@ -105,7 +107,10 @@ int uvrt_generate(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength
 int uvrt_extend(uvrt_ctx* ctx, int64_t nRays);
 /* accumulate.cl:4-14 */
 int uvrt_accumulate(uvrt_ctx* ctx, float duration);
-/* RayTracer::ComputeSingleLightDosageMap (raytracer.cpp:75-88): generate -> extend -> accumulate */
+/* RayTracer::ComputeSingleLightDosageMap (raytracer.cpp:75-88): generate -> extend -> accumulate.
+ * Asynchronous like Kernel::Run; consecutive calls overlap on the device (generate of the next launch and the
+ * tail of the previous extend run next to the current extend), results are as if run back to back.
+ * UVRT_BUF_COUNTS is zero again afterwards (accumulate.cl:13). */
 int uvrt_trace(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, float duration,
                int64_t firstRay, int64_t nRays, uint32_t seedIn);
 /* Same without the accumulate step (for launches split over several GPUs: the partial counts
