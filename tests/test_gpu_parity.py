@@ -725,3 +725,121 @@ def test_stage_calls_and_trace_share_the_count_buffer(uv, ctx, room):
         second = ctx.read(uv.BUF.COUNTS).astype(np.float64)
         assert np.array_equal(total, (first + second) * 2.5)
     ctx.reset(True)
+
+
+# ---- reference-derived goldens of the benchmarked configurations (tests/golden/make_golden_runs.py) ----------
+def _run_golden(route):
+    import json
+    return json.load(open(os.path.join(T.ROOT, "tests", "golden", "route_runs.json")))["runs"][route]
+
+
+@pytest.mark.parametrize("route", ["route", "lange_route"])
+def test_default_run_matches_reference_golden(uv, room, route):
+    """BASELINE configs[1] (route.xml) and the config-2 substitute (lange_route.xml) at FULL size: 2^25 photons x
+    10 iterations = 120 launches of 2,796,202 rays = 335,544,240 rays through RayTracer, compared after every
+    iteration with what the reference's own compiled sources produced (photon map, max map, dose, colours, SEED)."""
+    g = _run_golden(route)
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_mesh("testroomopt")
+    sim.init(route)
+    p = sim.params
+    assert p.photonCount == 1 << 25 and p.maxIterations == 10 and p.photonsPerLight == g["photonsPerLight"]
+    assert int(np.float32(p.lightIntensity).view(np.uint32)) == g["lightIntensity_bits"]
+    sim.reset_dosage_map()
+    c = sim.ctx
+    for it in range(10):
+        finished = sim.tick()
+        a = g["after_iteration"][it]
+        got = (f"{T.fnv(c.read(uv.BUF.SUM)):016x}", f"{T.fnv(c.read(uv.BUF.MAX)):016x}",
+               f"{T.fnv(sim.read_dose()):016x}", f"{T.fnv(c.read(uv.BUF.COLOR)):016x}", sim.params.seedState)
+        assert got == (a["fnv_photonMap"], a["fnv_maxPhotonMap"], a["fnv_dose"], a["fnv_color"], a["seed"]), f"iteration {it + 1}"
+    assert finished is False and sim.tick() is True          # the eleventh tick only notices that the run is over
+    assert sim.rays_traced() == g["rays"] == 335_544_240
+    dose = sim.read_dose()
+    assert [int(v) for v in dose[:8].view(np.uint32)] == g["after_iteration"][9]["dose_head_bits"]
+    sim.close()
+
+
+def test_every_launch_of_the_default_run_matches_reference_counts(uv, ctx, room):
+    """The 120 count vectors of the default run (route.xml), launch by launch through the stage API with the
+    golden SEED chain: hits and FNV of the integer counts equal the compiled reference's for every launch."""
+    g = _run_golden("route")
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_route("route")
+    pos, p = sim.positions, sim.params
+    sim.close()
+    f32 = np.float32
+    P = g["photonsPerLight"]
+    for k in range(120):
+        x, y, _ = pos[k % 12]
+        lp = (f32(x), f32(f32(room[3]) + f32(p.lightHeight)), f32(y))
+        ctx.reset(False)
+        ctx.trace_counts(lp, p.lightLength, 0, P, g["seed_chain"][k])
+        counts = ctx.read(uv.BUF.COUNTS)
+        assert int(counts.sum()) == g["hits_per_launch"][k], f"launch {k}"
+        assert f"{T.fnv(counts):016x}" == g["fnv_counts_per_launch"][k], f"launch {k}"
+    ctx.reset(True)
+
+
+@pytest.mark.parametrize("n_tris", [1_000_000, 10_000_000])
+def test_soup_matches_reference_golden(uv, n_tris):
+    """BASELINE config 5 at full size (10 M triangles) and at 1 M: device-built BVH, 1e6-ray launches; triIdx,
+    per-ray (dist, triID) and integer counts hash-equal to the reference's builder + extend kernel
+    (tests/golden/soup.json)."""
+    import json
+    import sys as _sys
+    _sys.path.insert(0, T.ROOT + "/tools")
+    from soup import make_soup, soup_route
+    g = json.load(open(os.path.join(T.ROOT, "tests", "golden", "soup.json")))["scenes"][str(n_tris)]
+    c = uv.Context(0)
+    tris, nodes, tri_idx = c.build_bvh(make_soup(n_tris))
+    assert f"{T.fnv(tri_idx):016x}" == g["fnv_triIdx"]
+    c.upload_scene(tris, nodes, tri_idx)
+    del tris, nodes
+    route = soup_route()
+    for key, gl in g["launch"].items():
+        x, z, _ = route[gl["position"]]
+        lp = (np.float32(x), np.float32(0.5), np.float32(z))
+        c.reset(False)
+        c.trace_counts(lp, 1.0, 0, gl["rays"], gl["seed_in"])
+        rays = c.read(uv.BUF.RAYS, gl["rays"])
+        counts = c.read(uv.BUF.COUNTS)
+        assert int(counts.sum()) == gl["hits"], key
+        assert f"{int(T.oracle().orc_fnv_hits(T.ptr(rays), gl['rays'])):016x}" == gl["fnv_hits"], key
+        assert f"{T.fnv(counts):016x}" == gl["fnv_counts"], key
+        assert int(c.seed_chain([lp], 1.0, gl["seed_in"])[1]) == gl["seed_out"]
+    c.close()
+
+
+def test_cuda_path_against_the_compiled_reference_directly(uv, ctx, room):
+    """Where oracle/_ref/libuvrt_ref.so travelled to the box: one launch compared with the reference's own
+    kernel sources directly (not through the C port): rays, closest hits, counts, maps, dose, colours."""
+    if not T.ref_available():
+        pytest.skip("oracle/_ref/libuvrt_ref.so is not on this box")
+    R = T.ref()
+    tris, nodes, tri_idx, floor = room
+    n, P, f32 = tris.shape[0], 400_000, np.float32
+    lp = (f32(0.51000142), f32(f32(floor) + f32(0.6)), f32(-0.25500044))
+    want = np.zeros(P, dtype=T.RAY_DT)
+    so = C.c_uint(0)
+    R.ref_generate(T.ptr(want), 0, P, lp[0], lp[1], lp[2], f32(1.0), 99, C.byref(so))
+    ctx.reset(True)
+    ctx.generate(lp, 1.0, 0, P, 99)
+    assert ctx.read(uv.BUF.RAYS, P).tobytes() == want.tobytes()
+    temp = np.zeros(n, dtype=np.int32)
+    R.ref_extend(T.ptr(temp), T.ptr(tris), T.ptr(want), T.ptr(nodes), T.ptr(tri_idx), P, n, 0)
+    ctx.extend(P)
+    assert ctx.read(uv.BUF.RAYS, P).tobytes() == want.tobytes()
+    assert np.array_equal(ctx.read(uv.BUF.COUNTS), temp)
+    pm, mx = np.zeros(n), np.zeros(n)
+    R.ref_accumulate(T.ptr(pm), T.ptr(mx), T.ptr(temp), f32(37.5), n)
+    ctx.accumulate(37.5)
+    assert ctx.read(uv.BUF.SUM).tobytes() == pm.tobytes() and ctx.read(uv.BUF.MAX).tobytes() == mx.tobytes()
+    dose, col = np.zeros(n, dtype=np.float32), np.zeros((n, 9), dtype=np.float32)
+    R.ref_compute_dosage(T.ptr(pm), T.ptr(dose), T.ptr(tris), P, f32(44.331842), n)
+    R.ref_dosage_to_color(T.ptr(dose), T.ptr(col), f32(100.0), 0, n)
+    ctx.shade(0, P, 44.331842)
+    ctx.color(100.0, 0)
+    assert ctx.read(uv.BUF.DOSE).tobytes() == dose.tobytes() and ctx.read(uv.BUF.COLOR).tobytes() == col.tobytes()
+    assert int(ctx.seed_chain([lp], 1.0, 99)[1]) == so.value
+    ctx.reset(True)

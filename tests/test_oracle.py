@@ -136,6 +136,55 @@ def test_oracle_full_pass_matches_golden(checkers, room, golden, uv):
     assert int((dose == 0).sum()) == g["unlit"]
 
 
+def test_oracle_first_route_pass_matches_run_golden(checkers, room, uv):
+    """BASELINE configs[1] itself: the first of the ten passes over the shipped route.xml (12 x 2,796,202 rays,
+    lamp height 0.6, power 443.3) against tests/golden/route_runs.json, which the reference's own compiled
+    sources produced for the whole 10-iteration run (tests/golden/make_golden_runs.py)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(T.ROOT, "tests", "golden", "route_runs.json")))["runs"]["route"]
+    tris, nodes, tri_idx, floor = room
+    O = checkers.oracle()
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_route("route")
+    pos, p = sim.positions, sim.params
+    sim.close()
+    P, n, f32 = int(p.photonsPerLight), tris.shape[0], np.float32
+    assert P == g["photonsPerLight"] and len(pos) == g["positions"]
+    assert int(f32(p.lightHeight).view(np.uint32)) == g["lightHeight_bits"]
+    pm, mx, temp = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32)
+    rays = np.zeros(P, dtype=T.RAY_DT)
+    seed = 0
+    for k, (x, y, dur) in enumerate(pos):
+        so = C.c_uint32(0)
+        O.orc_generate(T.ptr(rays), 0, P, f32(x), f32(f32(floor) + f32(p.lightHeight)), f32(y), f32(p.lightLength), seed, C.byref(so))
+        O.orc_extend(T.ptr(temp), T.ptr(tris), T.ptr(rays), T.ptr(nodes), T.ptr(tri_idx), P, 0, None)
+        assert int(temp.sum()) == g["hits_per_launch"][k]
+        assert f"{T.fnv(temp):016x}" == g["fnv_counts_per_launch"][k]
+        O.orc_accumulate(T.ptr(pm), T.ptr(mx), T.ptr(temp), f32(dur), n)
+        seed = int(so.value)
+        assert seed == g["seed_chain"][k + 1]
+    a = g["after_iteration"][0]
+    dose = np.zeros(n, dtype=np.float32)
+    O.orc_compute_dosage(T.ptr(pm), T.ptr(dose), T.ptr(tris), P, f32(f32(p.lightIntensity) * f32(0.1)), n)
+    col = np.zeros((n, 9), dtype=np.float32)
+    O.orc_dosage_to_color(T.ptr(dose), T.ptr(col), f32(p.minDosage), 0, n)
+    assert (f"{T.fnv(pm):016x}", f"{T.fnv(mx):016x}", f"{T.fnv(dose):016x}", f"{T.fnv(col):016x}") == \
+           (a["fnv_photonMap"], a["fnv_maxPhotonMap"], a["fnv_dose"], a["fnv_color"])
+
+
+def test_run_goldens_agree_with_appendix_c(golden):
+    """The 10-iteration golden of lange_route starts with the pass SURVEY App. C.2 records."""
+    import json
+    import os
+    g = json.load(open(os.path.join(T.ROOT, "tests", "golden", "route_runs.json")))["runs"]["lange_route"]
+    c2 = golden["pass_lange_route"]
+    assert g["seed_chain"][:13] == c2["seed_chain"] and g["hits_per_launch"][:12] == c2["hits_per_position"]
+    a = g["after_iteration"][0]
+    assert (a["fnv_photonMap"], a["fnv_maxPhotonMap"], a["fnv_dose"], a["fnv_color"]) == \
+           (c2["fnv_photonMap"], c2["fnv_maxPhotonMap"], c2["fnv_dose"], c2["fnv_color"])
+
+
 def test_bvh_closest_hit_equals_brute_force(checkers, room):
     """Slab-test false negatives would show up as BVH hits farther than the brute-force hit."""
     tris, nodes, tri_idx, floor = room
