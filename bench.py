@@ -8,18 +8,27 @@ configuration "testroomopt.glb full route.xml dose map" (configs[1]).
 A *step* is one pass over the route, what one frame of the reference's MyApp::Tick computes
 (myapp.cpp:156-175): for each of the 12 lamp positions of positions/route.xml one launch of
 P = 2,796,202 rays (generate, extend, accumulate), then computeDosage + dosageToColor.
-With N GPUs a step is N such passes (one per GPU on average: launch k of the run goes to rank
-k mod N), i.e. weak scaling; the per-GPU photon maps are combined by ONE NCCL all-reduce at the end
-of the run (inside the timed region).
+With N GPUs a step is N such passes (weak scaling): the launches are dealt to the ranks
+(RayTracer::ShardOwner), every rank counts into its rows of a count matrix, ONE ncclAllReduce per
+window of launches sums the integer rows and every rank folds them in launch order.
 
   value     device-timed (CUDA events on the backend's stream, max over ranks), scene resident in HBM
+  sustained the same step looped for >= 5 s with the clock sampler running (warm die)
   e2e       the same work through the reference-facing RayTracer interface with HOST buffers:
             every step uploads the scene (Tri/BVHNode/triIdx arrays -> pinned staging -> device),
             resets the maps, traces, shades and reads the dose map back; wall clock
   roofline  extend kernel: algorithmic bytes B_ray = 44 + 64*I + 52*T per ray (I, T
             measured by the oracle's traversal counters on this very workload and committed in
             profiles/traversal_stats_route.json) over the event-timed average launch duration
-            (overlapping launches charged once), against the measured HBM copy bandwidth
+            (overlapping launches charged once), against the measured HBM copy bandwidth.  The scene is
+            cache resident, so that fraction exceeds 1; `binding` names the resource that does bound the
+            kernel, from the committed ncu capture (profiles/extend_ncu_metrics.json + raw CSV), and
+            `hbm_actual_frac` is the DRAM traffic ncu measured over the same launch time
+  parity    after the timed regions the DEFAULT RUN of the configuration (route.xml as shipped: 10
+            iterations, 335,544,240 rays) is executed once more from SEED 0, shared between the N ranks,
+            and the FNV-1a-64 of its dose map is compared with the golden the reference's own compiled
+            sources produced (tests/golden/route_runs.json): "golden" or "mismatch".  The same run,
+            wall clock, is the route dose-map time; rank 0 repeats it alone for strong_efficiency.
   cpu_baseline  the reference's own kernels (oracle/_ref, compiled from its sources) or the C port,
             OpenMP over all host cores, on one pass over the route
 
@@ -45,6 +54,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 WORKLOAD = "testroomopt.glb full route.xml dose map"
 ROOM, ROUTE = "testroomopt", "route"
 DATA = os.path.join(ROOT, "data")
+DATA_NOTE = ("real: the reference's own assets (rooms/testroomopt.glb, positions/route.xml); rays drawn by the reference's "
+             "RNG (generate.cl) from SEED 0")
 
 
 def load_peaks():
@@ -57,6 +68,21 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def workload_config(n_tris, L, P, n_gpus):
+    """The workload both arms run -- identical keys and values for `--impl uvrt` and `--impl reference`."""
+    return {"workload": WORKLOAD, "room": ROOM + ".glb", "route": ROUTE + ".xml", "triangles": int(n_tris), "positions": int(L),
+            "rays_per_launch": int(P), "rays_per_step": int(n_gpus * L * P),
+            "timed": "generate+extend+accumulate per position, computeDosage+dosageToColor per pass",
+            "l2": "flushed before every step (256 MiB memset on the same stream)"}
+
+
+def fnv1a64(a):
+    h = 1469598103934665603
+    for b in np.ascontiguousarray(a).view(np.uint8).reshape(-1).tobytes():
+        h = ((h ^ b) * 1099511628211) & 0xffffffffffffffff
+    return f"{h:016x}"
+
+
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -67,35 +93,38 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
-        self.t0 = self.t1 = None
+        self.windows = {}
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def begin(self):
-        self.t0 = time.time()
+    def begin(self, name="timed"):
+        self.windows[name] = [time.time(), None]
 
-    def end(self):
-        self.t1 = time.time()
+    def end(self, name="timed"):
+        self.windows[name][1] = time.time()
 
     def stop(self):
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
-        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.1] or [r for _, r in self.rows]
-        sm, mx, reasons = [], [], set()
+
+    def summary(self, name="timed"):
+        t0, t1 = self.windows.get(name, (None, None))
+        inside = [r for (t, r) in self.rows if t0 is not None and t0 <= t <= (t1 or t0) + 0.06] or [r for _, r in self.rows[-2:]]
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in inside:
             f = [x.strip() for x in r.split(",")]
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
             except Exception:
                 continue
             for n, v in zip(names, f[3:7]):
@@ -103,14 +132,23 @@ class ClockSampler:
                     reasons.add(n)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's kernels on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_route_pass(room, positions, params, rays_per_launch, seed=0, want_counters=False):
-    """One pass over the route on the CPU.  Returns (seconds, rays, kind, cores, counters)."""
+def host_threads():
+    """All the host's cores, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_route_pass(room, positions, params, rays_per_launch, seed=0, want_counters=False, threads=0):
+    """One pass over the route on the CPU.  Returns (seconds, rays, kind, cores, counters, seed)."""
     import uvrt_testlib as T
     tris, nodes, tri_idx, floor = room
     n = tris.shape[0]
@@ -120,6 +158,10 @@ def cpu_route_pass(room, positions, params, rays_per_launch, seed=0, want_counte
         T.build_checkers()
     O = T.oracle()
     R = T.ref() if use_ref else None
+    threads = threads or host_threads()
+    O.orc_set_num_threads(threads)
+    if R is not None:
+        R.ref_set_num_threads(threads)
     pm, mx, temp = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32)
     dose = np.zeros(n, dtype=np.float32)
     col = np.zeros((n, 9), dtype=np.float32)
@@ -131,13 +173,13 @@ def cpu_route_pass(room, positions, params, rays_per_launch, seed=0, want_counte
         if use_ref:
             so = C.c_uint(0)
             R.ref_generate(T.ptr(rays), 0, rays_per_launch, lp[0], lp[1], lp[2], f32(params.lightLength), seed, C.byref(so))
-            R.ref_extend(T.ptr(temp), T.ptr(tris), T.ptr(rays), T.ptr(nodes), T.ptr(tri_idx), rays_per_launch, n, 0)
+            R.ref_extend(T.ptr(temp), T.ptr(tris), T.ptr(rays), T.ptr(nodes), T.ptr(tri_idx), rays_per_launch, n, threads)
             R.ref_accumulate(T.ptr(pm), T.ptr(mx), T.ptr(temp), f32(dur), n)
         else:
             so = C.c_uint32(0)
             cnt = T.Counters()
             O.orc_generate(T.ptr(rays), 0, rays_per_launch, lp[0], lp[1], lp[2], f32(params.lightLength), seed, C.byref(so))
-            O.orc_extend(T.ptr(temp), T.ptr(tris), T.ptr(rays), T.ptr(nodes), T.ptr(tri_idx), rays_per_launch, 0, C.byref(cnt))
+            O.orc_extend(T.ptr(temp), T.ptr(tris), T.ptr(rays), T.ptr(nodes), T.ptr(tri_idx), rays_per_launch, threads, C.byref(cnt))
             O.orc_accumulate(T.ptr(pm), T.ptr(mx), T.ptr(temp), f32(dur), n)
             for k in ("rays", "innerVisits", "leafVisits", "triTests", "hits"):
                 setattr(tot, k, getattr(tot, k) + getattr(cnt, k))
@@ -151,13 +193,13 @@ def cpu_route_pass(room, positions, params, rays_per_launch, seed=0, want_counte
         O.orc_compute_dosage(T.ptr(pm), T.ptr(dose), T.ptr(tris), ppl, power, n)
         O.orc_dosage_to_color(T.ptr(dose), T.ptr(col), f32(params.minDosage), 0, n)
     dt = time.perf_counter() - t0
-    cores = int(O.orc_num_threads())
-    return dt, rays_per_launch * len(positions), ("reference" if use_ref else "port"), cores, tot, seed
+    cores = int(R.ref_num_threads() if use_ref else O.orc_num_threads())
+    return dt, rays_per_launch * len(positions), ("reference" if use_ref else "port"), cores, tot, seed, dose
 
 
 def traversal_stats(room, positions, params, sample_per_launch=200_000):
     """I (inner-node visits per ray) and T (triangle tests per ray) for B_ray, from the oracle's counters."""
-    _, rays, _, _, cnt, _ = cpu_route_pass(room, positions, params, sample_per_launch, want_counters=True)
+    _, rays, _, _, cnt, _, _ = cpu_route_pass(room, positions, params, sample_per_launch, want_counters=True)
     return cnt.innerVisits / rays, cnt.triTests / rays
 
 
@@ -170,38 +212,61 @@ def load_room_host(uv, device=0):
     return sim, (tris, nodes, tri_idx, floor)
 
 
+def golden_route():
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "route_runs.json")))["runs"][ROUTE]
+    except Exception:
+        return None
+
+
 def run_reference_arm(args):
     """The reference's CPU implementation of the path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    threads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)      # before libgomp is loaded; the explicit *_set_num_threads calls follow
     uv = importlib.import_module("small-project-uv-robot-ray-tracer_b200")
     sim, room = load_room_host(uv)       # host-side loading only: no GPU, none of the CUDA path
     pos, p = sim.positions, sim.params
-    # bounded sample: every step walks the whole route with 1/16 of the photons per position
-    per_launch = (p.photonsPerLight // 16) & ~1
+    L, P = len(pos), int(p.photonsPerLight)
+    # one step = one FULL pass over the route (12 positions x 2,796,202 rays); at --gpus N the GPU arm's step is N such
+    # passes: the CPU arm's step stays one pass (a bounded sample of the same workload; Mrays/s is a rate)
     seed = 0
-    for _ in range(args.warmup):
-        _, _, kind, cores, _, seed = cpu_route_pass(room, pos, p, per_launch, seed)
+    warm = args.warmup
+    t_first = None
+    done = 0
+    while done < warm:
+        dt, _, kind, cores, _, seed, dose = cpu_route_pass(room, pos, p, P, seed, threads=threads)
+        done += 1
+        if t_first is None:
+            t_first = dt
+            if dt * (args.steps + warm) > 240.0:      # a slow host: keep the whole run within a few minutes
+                warm = 1
     t = 0.0
     rays = 0
-    for _ in range(args.steps):
-        dt, r, kind, cores, _, seed = cpu_route_pass(room, pos, p, per_launch, seed)
+    for k in range(args.steps):
+        dt, r, kind, cores, _, seed, dose = cpu_route_pass(room, pos, p, P, seed, threads=threads)
         t += dt
         rays += r
     value = rays / t / 1e6
-    sample = f"{len(pos)} positions x {per_launch} rays per step (1/16 of the photons per position), {args.steps} steps"
+    # parity of the arm itself: one pass from SEED 0 is iteration 1 of the golden run
+    g = golden_route()
+    _, _, _, _, _, _, dose0 = cpu_route_pass(room, pos, p, P, 0, threads=threads)
+    fnv = fnv1a64(dose0)
+    sample = f"one pass over {ROUTE}.xml per step: {L} positions x {P} rays = {L * P} rays (full photons per position), {args.steps} steps"
     line = {
         "impl": "reference", "metric": "Mrays/s (extend+shade)", "value": round(value, 3), "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t / args.steps, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "room": ROOM + ".glb", "route": ROUTE + ".xml", "triangles": int(room[0].shape[0]),
-                   "positions": int(len(pos)), "rays_per_launch_full": int(p.photonsPerLight),
-                   "timed": "generate+extend+accumulate per position, then computeDosage+dosageToColor"},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": DATA_NOTE,
+        "config": workload_config(room[0].shape[0], L, P, args.gpus),
         "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference kernels (cl/*.cl) and bvh.cpp compiled for the host by oracle/build_ref.sh; no OpenCL runtime exists on the box",
+        "parity": {"dose_fnv_iteration1": fnv, "golden": g["after_iteration"][0]["fnv_dose"] if g else None,
+                   "result": "golden" if g and fnv == g["after_iteration"][0]["fnv_dose"] else "mismatch"},
+        "note": "reference kernels (cl/*.cl) and bvh.cpp compiled for the host by oracle/build_ref.sh, OpenMP over all host cores "
+                "(thread count set explicitly: launchers such as torchrun export OMP_NUM_THREADS=1); no OpenCL runtime exists on the box",
     }
     print(json.dumps(line), flush=True)
 
@@ -213,9 +278,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="uvrt", choices=["uvrt", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--sustain-s", type=float, default=5.0, help="length of the sustained loop (0: skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--write-traversal-stats", action="store_true", help="re-measure I and T with the oracle's counters and commit them")
     ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--parts", type=int, default=0, help="ray ranges per launch of sharded runs (0: RayTracer::AutoParts)")
     ap.add_argument("--opt", action="append", default=[], help="backend option key=value (uvrt_set_option), repeatable")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -254,6 +321,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     if dist is not None:
         import torch
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -262,52 +337,68 @@ def main():
         dist.broadcast(idt, 0)
         ctx.comm_init(bytes(idt.cpu().tolist()), rank, world)
         sim.set_shard(rank, world)
+        sim.set_shard_parts(args.parts)
 
-    # ---- device-timed run: scene resident, K steps, one reduction + shade + read-back at the end ----
-    def run_steps(k_steps, timed):
+    # ---- device-timed run: scene resident, K steps; sharded: window folds as they fall + one at the end ----
+    def run_steps(k_steps, budget_s=None):
         sim.set_params(maxIterations=k_steps * n_gpus)
         sim.reset_dosage_map()
         ctx.sync()
-        total_ms = 0.0
+        total_ms, done = 0.0, 0
+        t_wall = time.perf_counter()
         for s in range(k_steps):
             ctx.flush_l2()                       # cold L2 at the start of every step
             ctx.mark(0)
-            for _ in range(n_gpus):              # n_gpus passes over the route, dealt out launch by launch
+            for _ in range(n_gpus):              # n_gpus passes over the route, dealt out over the ranks
                 sim.compute_dosage_map()         # RayTracer::ComputeDosageMap: asynchronous, like Kernel::Run
                 if n_gpus == 1:
                     sim.shade()                  # one GPU: shade after every pass, as MyApp::Tick does
-            if s == k_steps - 1 and n_gpus > 1:
-                sim.reduce()                     # the run's one all-reduce
+            last = s == k_steps - 1 or (budget_s is not None and time.perf_counter() - t_wall >= budget_s)
+            if last and n_gpus > 1:
+                sim.reduce()                     # all-reduce + fold of the rows still pending
                 sim.shade()
             ctx.mark(1)
             total_ms += ctx.elapsed_ms(0, 1)
-        return total_ms
+            done += 1
+            if last:
+                break
+        return total_ms, done
 
-    run_steps(max(args.warmup, 3), False)
+    run_steps(max(args.warmup, 3))
     ctx.set_option("stage_timing", 1)
     ctx.stage_time_reset()
     launches0 = ctx.launch_count()
     clocks = ClockSampler(local)
     barrier()
-    clocks.begin()
-    ms = run_steps(args.steps, True)
+    clocks.begin("timed")
+    ms, _ = run_steps(args.steps)
     barrier()
-    clocks.end()
-    clk = clocks.stop()
+    clocks.end("timed")
     launches = ctx.launch_count() - launches0
     ext_ms, ext_n = ctx.stage_time(uv.STAGE.EXTEND)
     stage_ms = {name: ctx.stage_time(getattr(uv.STAGE, name))[0] for name in
                 ("GENERATE", "BIN", "EXTEND", "ACCUMULATE", "SHADE", "COLOR", "RESET")}
     ctx.set_option("stage_timing", 0)
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms)
     total_rays = args.steps * n_gpus * rays_per_pass
     value = total_rays / (ms * 1e-3) / 1e6
-    dose = sim.read_dose()
-    traced_this_rank = sim.rays_traced()
+
+    # ---- sustained: the same step looped for >= sustain_s seconds, clocks sampled inside ----
+    sustained = None
+    if args.sustain_s > 0:
+        est_steps = int(args.sustain_s * 1e3 / max(ms / args.steps, 1e-3)) + 1
+        if dist is not None:             # all ranks must run the same number of steps
+            est_steps = int(max_over_ranks(float(est_steps)))
+        barrier()
+        clocks.begin("sustained")
+        t0 = time.perf_counter()
+        s_ms, s_steps = run_steps(est_steps)
+        barrier()
+        s_wall = time.perf_counter() - t0
+        clocks.end("sustained")
+        s_ms = max_over_ranks(s_ms)
+        sustained = {"value": round(s_steps * n_gpus * rays_per_pass / (s_ms * 1e-3) / 1e6, 1), "unit": "Mrays/s", "steps": s_steps,
+                     "device_s": round(s_ms * 1e-3, 3), "wall_s": round(s_wall, 3), "ms_per_step": round(s_ms / s_steps, 4)}
 
     # ---- end to end through the RayTracer interface with host buffers ----
     tris_h, nodes_h, idx_h, _ = room
@@ -327,32 +418,49 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        d = e2e_step()
+        e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        import torch
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = e2e_steps * n_gpus * rays_per_pass / e2e_s / 1e6
     h2d = ctx.scene_upload_bytes() + L * 12
     d2h = n_tris * 4
 
-    # ---- whole default run (10 iterations), wall clock: the "route dose-map time" ----
-    # (N GPUs: the 120 launches of the run are dealt over the ranks, one all-reduce at the end -- strong scaling)
+    # ---- the default run (10 iterations) from SEED 0: parity against the golden + the "route dose-map time" ----
+    # (N GPUs: the 120 launches of the run -- cut into ray ranges when that evens out the load -- are shared between
+    #  the ranks, one all-reduce of the count matrix at the end: strong scaling)
     sim.set_params(maxIterations=10)
     sim.run()                                            # warm-up (ray buffers of this size, NCCL channels)
+    sim.set_seed(0)
     barrier()
     t0 = time.perf_counter()
-    sim.run()
-    route_s = time.perf_counter() - t0
-    if dist is not None:
+    dose = sim.run()
+    route_ms = max_over_ranks(time.perf_counter() - t0) * 1e3
+    parts_in_effect = sim.shard_parts()
+    g = golden_route()
+    dose_fnv = fnv1a64(dose)
+    want_fnv = g["after_iteration"][9]["fnv_dose"] if g else None
+    parity_ok = 1.0 if (want_fnv is not None and dose_fnv == want_fnv and int(sim.params.seedState) == g["after_iteration"][9]["seed"]) else 0.0
+    if dist is not None:                                 # every rank must hold the golden map
         import torch
-        t = torch.tensor([route_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        route_s = float(t.item())
-    route_ms = route_s * 1e3
+        t = torch.tensor([parity_ok], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        parity_ok = float(t.item())
+    # strong-scaling reference: rank 0 alone, same run
+    solo_ms = None
+    if n_gpus > 1:
+        barrier()
+        if rank == 0:
+            sim.set_shard(0, 1)
+            sim.run()
+            sim.set_seed(0)
+            t0 = time.perf_counter()
+            d1 = sim.run()
+            solo_ms = (time.perf_counter() - t0) * 1e3
+            if fnv1a64(d1) != dose_fnv:
+                parity_ok = 0.0
+            sim.set_shard(rank, world)
+        barrier()
+    clocks.stop()
 
     if rank != 0:
         if dist is not None:
@@ -375,47 +483,66 @@ def main():
         I, T_ = float(st["inner_visits_per_ray"]), float(st["tri_tests_per_ray"])
     b_ray = 44.0 + 64.0 * I + 52.0 * T_
     ext_launch_ms = ext_ms / max(1, ext_n)
-    achieved = b_ray * P / (ext_launch_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "extend_dram_traffic.json")
-    if os.path.exists(tpath):
+    ext_rays = args.steps * n_gpus * rays_per_pass / n_gpus / max(1, ext_n)       # rays per extend launch on this rank
+    achieved = b_ray * ext_rays / (ext_launch_ms * 1e-3) / 1e9
+    traffic, binding, hbm_actual = None, None, None
+    mpath = os.path.join(ROOT, "profiles", "extend_ncu_metrics.json")
+    if os.path.exists(mpath):
         try:
-            traffic = json.load(open(tpath)).get("bytes_per_launch")
+            m = json.load(open(mpath))
+            traffic = m.get("bytes_per_launch")
+            binding = {"resource": "l1tex data-pipe wavefronts (gather of 32-byte node sectors into registers)",
+                       "frac": round(m["l1tex_data_pipe_wavefronts_pct"] / 100.0, 4), "issue_frac": round(m["issue_active_pct"] / 100.0, 4),
+                       "lanes_per_inst": m["lanes_per_inst"], "l1_hit_frac": round(m["l1_hit_pct"] / 100.0, 4),
+                       "l2_throughput_frac": round(m["l2_throughput_pct"] / 100.0, 4),
+                       "long_scoreboard_stalls_per_issue": m["long_scoreboard_stalls_per_issue"],
+                       "kernel_us_under_ncu": m["duration_us"], "source": "profiles/extend_ncu_metrics.json <- profiles/" + str(m.get("raw_csv")) +
+                       " (ncu --set full --clock-control none inside this bench.py; " + str(m.get("source")) + ")"}
+            if traffic:
+                hbm_actual = traffic / (ext_launch_ms * 1e-3) / 1e9 / peak
         except Exception:
-            traffic = None
+            pass
 
     line = {
         "metric": "Mrays/s (extend+shade)", "value": round(value, 1), "unit": "Mrays/s", "n_gpus": n_gpus,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "room": ROOM + ".glb", "route": ROUTE + ".xml", "triangles": int(n_tris),
-                   "positions": int(L), "rays_per_launch": int(P), "rays_per_step": int(n_gpus * rays_per_pass),
-                   "timed": "generate+bin+extend+accumulate per position, computeDosage+dosageToColor (and the all-reduce) at the end of the run",
-                   "l2": "flushed before every step (256 MiB memset on the same stream)",
-                   "extend_variant": ctx.get_option("extend_variant"), "bin_rays": ctx.get_option("bin_rays"),
-                   "pipeline": ctx.get_option("pipeline"),
-                   "parallelism": f"launches dealt round-robin to {n_gpus} GPU(s), one NCCL all-reduce per run"},
-        "clocks": clk,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": DATA_NOTE,
+        "config": workload_config(n_tris, L, P, n_gpus),
+        "impl_config": {"extend_variant": ctx.get_option("extend_variant"), "bin_rays": ctx.get_option("bin_rays"),
+                        "pipeline": ctx.get_option("pipeline"), "overlap_extend": ctx.get_option("overlap_extend"),
+                        "parallelism": ("one GPU" if n_gpus == 1 else
+                                        f"launches shared between {n_gpus} ranks (RayTracer::ShardOwner), integer count matrix, one ncclAllReduce "
+                                        f"per window + fold in launch order; route run: {parts_in_effect} ray range(s) per launch")},
+        "clocks": clocks.summary("timed"),
+        "sustained": (dict(sustained, clocks=clocks.summary("sustained")) if sustained else None),
         "e2e": {"value": round(e2e_value, 1), "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3),
-                "what": "upload_scene(host arrays) + ResetDosageMap + ComputeDosageMap + Shade + ReadDosageMap, wall clock"},
+                "what": "upload_scene(host arrays) + ResetDosageMap + ComputeDosageMap + (Reduce) + Shade + ReadDosageMap, wall clock"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "kernel": "extend", "launch_ms": round(ext_launch_ms, 4),
+                     "traffic": traffic, "hbm_actual_frac": (round(hbm_actual, 4) if hbm_actual is not None else None),
+                     "binding": binding, "kernel": "extend", "launch_ms": round(ext_launch_ms, 4), "rays_per_launch": int(round(ext_rays)),
                      "bytes_per_ray": round(b_ray, 1), "inner_visits_per_ray": round(I, 3), "tri_tests_per_ray": round(T_, 3),
                      "peak_source": peak_src,
-                     "note": "scene (6 MB) is L2/L1 resident: the HBM figure is the contract's denominator, not the binding limit (see DESIGN.md)"},
+                     "note": "the 8.6 MB scene is L1/L2 resident: the HBM-over-B_ray figure is the contract's denominator and exceeds 1; "
+                             "the kernel is bound by `binding.resource` and by instruction issue (DESIGN.md section 4)"},
         "stage_ms_per_step": {k.lower(): round(v / args.steps, 4) for k, v in stage_ms.items()},
-        "extend_mrays_s": round(P / ext_launch_ms / 1e3, 1),
+        "extend_mrays_s": round(ext_rays / ext_launch_ms / 1e3, 1),
         "route_dose_map_ms": round(route_ms, 2),
-        "route_dose_map": "route.xml as shipped: 10 iterations x 12 positions x 2,796,202 rays, ResetDosageMap .. dose map on the host, wall clock, max over ranks",
-        "dose_checksum": {"mean": float(np.mean(dose, dtype=np.float64)), "max": float(dose.max())},
+        "route_dose_map": "route.xml as shipped: 10 iterations x 12 positions x 2,796,202 rays from SEED 0, ResetDosageMap .. dose map on the host, "
+                          "wall clock, max over ranks",
+        "parity": {"result": "golden" if parity_ok == 1.0 else "mismatch", "dose_fnv": dose_fnv, "golden_dose_fnv": want_fnv,
+                   "what": f"the route dose-map run above (335,544,240 rays shared between {n_gpus} GPU(s)) against tests/golden/route_runs.json, "
+                           "produced by the reference's own compiled sources; every rank holds the map"},
     }
+    if solo_ms is not None:
+        line["route_dose_map_ms_1gpu"] = round(solo_ms, 2)
+        line["strong_efficiency"] = round(solo_ms / (n_gpus * route_ms), 4)
     if not args.no_cpu and n_gpus == 1:
         # (rank 0, N = 1 only: under torchrun the host threads are shared with the other ranks)
         # bounded CPU sample: exactly one step of the GPU workload (one pass over the route)
         per_launch = P
-        dt, rays, kind, cores, _, _ = cpu_route_pass(room, pos, p, per_launch)
+        dt, rays, kind, cores, _, _, _ = cpu_route_pass(room, pos, p, per_launch)
         line["cpu_baseline"] = {"value": round(rays / dt / 1e6, 3), "unit": "Mrays/s", "cores": cores, "kind": kind,
                                 "sample": f"one pass over {ROUTE}.xml, {L} positions x {per_launch} rays ({rays} rays, {dt:.1f} s)"}
     print(json.dumps(line), flush=True)

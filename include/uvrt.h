@@ -51,7 +51,9 @@ typedef enum uvrt_buffer {
     UVRT_BUF_DOSE = 4,   /* dosageBuffer:        nTris x f32                                      */
     UVRT_BUF_COLOR = 5,  /* colorBuffer:         nTris x 9 x f32 (plain buffer instead of GL VBO) */
     UVRT_BUF_PAIRS = 6,  /* diagnostic, read only: traversal layout, 64 B per inner node   */
-    UVRT_BUF_WTRIS = 7   /* diagnostic, read only: leaf-ordered triangles, 64 B per slot                  */
+    UVRT_BUF_WTRIS = 7,  /* diagnostic, read only: leaf-ordered triangles, 64 B per slot                  */
+    UVRT_BUF_MATRIX = 8  /* count matrix of uvrt_matrix_begin: rows x nTris x i32 (read: waits for the traces in
+                            flight; write: lets a caller without NCCL exchange the rows by its own means)  */
 } uvrt_buffer;
 
 /* Stage ids for uvrt_stage_time */
@@ -143,18 +145,37 @@ int uvrt_reduce(uvrt_ctx* ctx);
 /* Sum of UVRT_BUF_COUNTS over all ranks (in place). */
 int uvrt_reduce_counts(uvrt_ctx* ctx);
 
+/* Count matrix: the exchange format of runs whose launches are shared between GPUs, whole or cut into ray
+ * ranges.  accumulate.cl:4-14 folds every launch's integer counts into an f64 sum and an
+ * f64 per-launch maximum, so per-GPU f64 maps can only be combined exactly when no launch is split and the
+ * count x duration products happen to add without rounding.  Instead every rank writes the counts of launch k
+ * (its share of the rays) into row k of a rows x nTris int32 matrix, the rows are summed over the ranks with
+ * ONE ncclAllReduce, and the fold replays accumulate row by row in launch order on every rank: photon map and
+ * max map are then bit-identical to the single-GPU run for any split and any durations.
+ *   uvrt_matrix_begin  sizes and zeroes the matrix (a run, or a window of a long run)
+ *   uvrt_trace_row     generate -> (bin) -> extend of rays [firstRay, firstRay + nRays) of a launch, counted in
+ *                      `row`; asynchronous, consecutive calls overlap like uvrt_trace
+ *   uvrt_matrix_fold   (reduce != 0 and a communicator exists: all-reduce of the first `rows` rows, then)
+ *                      UVRT_BUF_SUM += count x durations[r], UVRT_BUF_MAX = max(., count) for r = 0 .. rows-1 */
+int uvrt_matrix_begin(uvrt_ctx* ctx, int rows);
+int uvrt_trace_row(uvrt_ctx* ctx, int row, float lx, float ly, float lz, float lightLength,
+                   int64_t firstRay, int64_t nRays, uint32_t seedIn);
+int uvrt_matrix_fold(uvrt_ctx* ctx, const float* durations, int rows, int reduce);
+
 /* ---- tuning and measurement ------------------------------------------------------------- */
 /* Options (defaults are the measured best; everything else exists for A/B runs, see DESIGN.md section 4 and
  * profiles/r1_sweeps.md):
  *   "extend_variant"  kernel selection: 0/1/2 one thread per ray with IEEE / two-step / one-step (default) slab
- *                     division; 10..24 persistent warps with a global queue; 40..43 chunk-persistent warps
+ *                     division.  Builds with -DUVRT_EXPERIMENTS (`make EXPERIMENTS=1`, read-only option
+ *                     "experiments") also carry the rejected variants of profiles/r1_sweeps.md: 10..24 persistent
+ *                     warps with a global queue, 40..43 chunk-persistent warps
  *   "bin_rays"        1 (default): counting sort of the ray queue by direction / origin cell before extend;
  *                     "bin_y", "bin_t", "bin_p": the bin grid
  *   "pipeline"        1 (default): generate + bin of launch k+1 on a second stream next to extend k
  *   "overlap_extend"  1 (default): uvrt_trace alternates two extend streams / count buffers, so extend k+1 fills
  *                     the SMs that the last wave of extend k leaves idle
- *   "fetch_mode"      3 (default): rays, permutation, results bypass L1; 0 plain; 1/2 texture path; 4 evict_last
- *                     nodes; 5 SM-affine chunks
+ *   "fetch_mode"      3 (default): rays, permutation, results bypass L1; 0 plain (experiment builds: 1/2 texture
+ *                     path; 4 evict_last nodes; 5 SM-affine chunks)
  *   "host_repack"     0 (default): uvrt_upload_scene repacks the scene on the device; 1: on the host cores
  *   "stage_timing"    1: bracket every launch with CUDA events (uvrt_stage_time)
  *   "simple_cfg", "hist_mode", "refill", "chunk", "blocks_per_sm", "generic_octant", "carveout": sweep knobs
@@ -165,6 +186,10 @@ int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value);
  * uvrt_stage_time_reset (needs "stage_timing" = 1).  Synchronises. */
 int uvrt_stage_time(uvrt_ctx* ctx, uvrt_stage stage, double* ms, int64_t* launches);
 int uvrt_stage_time_reset(uvrt_ctx* ctx);
+/* Option "timeline" = 1 starts a log of every C-ABI call (host clock) and of every stage launch (host time of
+ * the enqueue, device start / stop from CUDA events); uvrt_timeline_dump writes it as JSON (synchronises).
+ * Every stage launch and API call is also an NVTX range (nvtx3, header only) for nsys / ncu --nvtx. */
+int uvrt_timeline_dump(uvrt_ctx* ctx, const char* path);
 /* Kernels launched by this context since creation. */
 int64_t uvrt_launch_count(const uvrt_ctx* ctx);
 /* Event timing on the context's stream (torch.cuda.Event only sees torch's stream). */

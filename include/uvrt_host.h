@@ -81,12 +81,22 @@ int uvrt_sim_tick(uvrt_sim* sim, int* finished);
 int uvrt_sim_run(uvrt_sim* sim, float* dose, int capacity);
 int uvrt_sim_calibrate(uvrt_sim* sim, float measurePower, float measureHeight, float measureDist, float* calibratedPower);
 int uvrt_sim_read_dose(uvrt_sim* sim, float* dst, int capacity);
-/* Work sharing over ranks (launch k goes to rank k % count) and the final cross-rank reduction. */
+/* Work sharing over ranks and the cross-rank reduction (RayTracer::shardRank/shardCount/shardParts, Reduce):
+ * every launch is cut into `parts` ray ranges (0 = chosen per run, 1 = whole launches), unit = launch * parts +
+ * part goes to rank uvrt_host_shard_owner(unit, positions * parts, count); the ranks' integer counts meet in a
+ * count matrix that uvrt_sim_reduce sums (one ncclAllReduce) and folds in launch order. */
 int uvrt_sim_set_shard(uvrt_sim* sim, int rank, int count);
+int uvrt_sim_set_shard_parts(uvrt_sim* sim, int parts);
+int uvrt_sim_shard_parts(const uvrt_sim* sim);           /* the value in effect for the next run */
 int uvrt_sim_reduce(uvrt_sim* sim);
-/* The rank that traces launch `launch` (counted over the whole run) of a route with `positions` lamp
- * positions on `ranks` GPUs (RayTracer::ShardOwner). */
-int uvrt_host_shard_owner(long long launch, int positions, int ranks);
+/* The rank that traces unit `unit` (counted over the whole run) of a run with `unitsPerPass` units per pass on
+ * `ranks` GPUs (RayTracer::ShardOwner). */
+int uvrt_host_shard_owner(long long unit, int unitsPerPass, int ranks);
+/* The device-side SEED (generate.cl:6) the next launch will see; it survives ResetDosageMap like the
+ * reference's program-scope variable.  Setting it to 0 reproduces a freshly started application. */
+int uvrt_sim_set_seed(uvrt_sim* sim, uint32_t seed);
+/* SEED after a launch at (lx, ly, lz): work-item 0 of generate.cl:13-39 replayed on the host. */
+uint32_t uvrt_host_seed_after_launch(float lx, float ly, float lz, float lightLength, uint32_t seedIn);
 /* Result export: <basePath>.dose.f32 (float32 per triangle), .ply (per-vertex colours of dosageToColor),
  * .json (parameters).  Call after uvrt_sim_shade / uvrt_sim_run. */
 int uvrt_sim_save_dosage_map(uvrt_sim* sim, const char* basePath);

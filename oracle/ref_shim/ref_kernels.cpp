@@ -102,6 +102,15 @@ void ref_reset(double* photonMap, double* maxPhotonMap, int* temp, float* color9
     }
 }
 
+void ref_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int ref_num_threads(void)
 {
 #ifdef _OPENMP

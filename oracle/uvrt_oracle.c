@@ -355,6 +355,16 @@ uint64_t orc_fnv_hits(const orc_ray* rays, int64_t n)
     return h;
 }
 
+/* bench.py's CPU legs pin the thread count explicitly: launchers such as torchrun export OMP_NUM_THREADS=1 */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -20,7 +20,7 @@ class UvrtError(RuntimeError):
 
 
 class BUF:
-    RAYS, COUNTS, SUM, MAX, DOSE, COLOR, PAIRS, WTRIS = range(8)
+    RAYS, COUNTS, SUM, MAX, DOSE, COLOR, PAIRS, WTRIS, MATRIX = range(9)
 
 
 class STAGE:
@@ -103,6 +103,10 @@ def lib():
         "uvrt_comm_init": (i, [vp, vp, i, i]),
         "uvrt_reduce": (i, [vp]),
         "uvrt_reduce_counts": (i, [vp]),
+        "uvrt_matrix_begin": (i, [vp, i]),
+        "uvrt_trace_row": (i, [vp, i, f, f, f, f, i64, i64, u32]),
+        "uvrt_matrix_fold": (i, [vp, vp, i, i]),
+        "uvrt_timeline_dump": (i, [vp, C.c_char_p]),
         "uvrt_set_option": (i, [vp, C.c_char_p, i]),
         "uvrt_get_option": (i, [vp, C.c_char_p, C.POINTER(i)]),
         "uvrt_stage_time": (i, [vp, i, C.POINTER(C.c_double), C.POINTER(i64)]),
@@ -161,6 +165,10 @@ def host():
         "uvrt_sim_save_checkpoint": (i, [vp, C.c_char_p]),
         "uvrt_sim_load_checkpoint": (i, [vp, C.c_char_p]),
         "uvrt_sim_set_shard": (i, [vp, i, i]),
+        "uvrt_sim_set_shard_parts": (i, [vp, i]),
+        "uvrt_sim_shard_parts": (i, [vp]),
+        "uvrt_sim_set_seed": (i, [vp, C.c_uint32]),
+        "uvrt_host_seed_after_launch": (C.c_uint32, [f, f, f, f, C.c_uint32]),
         "uvrt_host_shard_owner": (i, [C.c_longlong, i, i]),
         "uvrt_sim_reduce": (i, [vp]),
         "uvrt_sim_ctx": (vp, [vp]),
@@ -287,6 +295,8 @@ class Context:
             out = np.zeros((max(self.scene_info()["inner"], 1), 16), dtype=np.uint32)
         elif what == BUF.WTRIS:
             out = np.zeros((n_rays if n_rays is not None else n, 16), dtype=np.uint32)
+        elif what == BUF.MATRIX:
+            out = np.zeros((n_rays, n), dtype=np.int32)        # n_rays = rows
         else:
             out = np.zeros((n, 9), dtype=np.float32)
         self.check(self.L.uvrt_read(self.h, what, _p(out), out.nbytes))
@@ -346,6 +356,19 @@ class Context:
 
     def reduce_counts(self):
         self.check(self.L.uvrt_reduce_counts(self.h))
+
+    def matrix_begin(self, rows):
+        self.check(self.L.uvrt_matrix_begin(self.h, rows))
+
+    def trace_row(self, row, lp, light_length, first_ray, n_rays, seed_in):
+        self.check(self.L.uvrt_trace_row(self.h, row, lp[0], lp[1], lp[2], light_length, first_ray, n_rays, seed_in))
+
+    def matrix_fold(self, durations, reduce=False):
+        d = np.ascontiguousarray(durations, dtype=np.float32)
+        self.check(self.L.uvrt_matrix_fold(self.h, _p(d), d.shape[0], int(reduce)))
+
+    def timeline_dump(self, path):
+        self.check(self.L.uvrt_timeline_dump(self.h, str(path).encode()))
 
 
 def comm_unique_id():
@@ -495,6 +518,15 @@ class Sim:
 
     def set_shard(self, rank, count):
         self.check(self.H.uvrt_sim_set_shard(self.h, rank, count))
+
+    def set_shard_parts(self, parts):
+        self.check(self.H.uvrt_sim_set_shard_parts(self.h, parts))
+
+    def shard_parts(self):
+        return int(self.H.uvrt_sim_shard_parts(self.h))
+
+    def set_seed(self, seed):
+        self.check(self.H.uvrt_sim_set_seed(self.h, seed))
 
     def reduce(self):
         self.check(self.H.uvrt_sim_reduce(self.h))

@@ -8,6 +8,7 @@
 #include "uvrt_scene_prep.cuh"
 
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler injects itself
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -184,7 +185,20 @@ struct uvrt_ctx {
     int simpleCfg = 1;        // 128 threads, <= 40 registers (48 resident warps per SM): fastest in the sweep
     int refill = 24;          // persistent kernels: refill when fewer lanes than this are busy
 
+    // count matrix (uvrt_matrix_*): one int32 row of nTris counters per launch of a run / window
+    int* dMatrix = nullptr;
+    size_t matrixCap = 0;                // capacity in int32 elements
+    int matrixRows = 0;
+    float* dDurations = nullptr;
+    int durCap = 0;
+
     // measurement
+    int timeline = 0;                    // option "timeline": host-side call log + device times of every stage launch
+    cudaEvent_t timelineOrigin = nullptr;
+    double timelineHost0 = 0;
+    struct ApiCall { const char* name; double t0, t1; };
+    std::vector<ApiCall> apiLog;
+    std::vector<double> timedHost;       // host time at which timed[i] was enqueued
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> freeEvents;
     cudaEvent_t marks[16] = {};
@@ -246,13 +260,23 @@ cudaEvent_t get_event(uvrt_ctx* ctx)
     return e;
 }
 
+double host_now_us()
+{
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+const char* const kStageNames[UVRT_STAGE_COUNT] = {"generate", "extend", "accumulate", "computeDosage", "dosageToColor", "reset", "bin"};
+
+// Brackets the launches of one stage: an NVTX range (visible in nsys / ncu --nvtx) and, with
+// "stage_timing" or "timeline" on, a pair of CUDA events on the launching stream.
 struct StageTimer {
     uvrt_ctx* ctx;
     TimedLaunch t{};
     bool on;
     cudaStream_t stream;
-    StageTimer(uvrt_ctx* c, int stage, cudaStream_t st = nullptr) : ctx(c), on(c->stageTiming != 0), stream(st ? st : c->stream)
+    StageTimer(uvrt_ctx* c, int stage, cudaStream_t st = nullptr) : ctx(c), on(c->stageTiming != 0 || c->timeline != 0), stream(st ? st : c->stream)
     {
+        nvtxRangePushA(stage >= 0 && stage < UVRT_STAGE_COUNT ? kStageNames[stage] : "stage");
         if (!on) return;
         t.stage = stage;
         t.start = get_event(c);
@@ -261,9 +285,28 @@ struct StageTimer {
     }
     ~StageTimer()
     {
+        nvtxRangePop();
         if (!on) return;
         cudaEventRecord(t.stop, stream);
         ctx->timed.push_back(t);
+        if (ctx->timeline) ctx->timedHost.push_back(host_now_us() - ctx->timelineHost0);
+    }
+};
+
+// One per C-ABI entry point that does work: NVTX range + (with "timeline") a host-side record of the call.
+struct ApiScope {
+    uvrt_ctx* ctx;
+    const char* name;
+    double t0 = 0;
+    ApiScope(uvrt_ctx* c, const char* n) : ctx(c), name(n)
+    {
+        nvtxRangePushA(n);
+        if (c && c->timeline) t0 = host_now_us() - c->timelineHost0;
+    }
+    ~ApiScope()
+    {
+        nvtxRangePop();
+        if (ctx && ctx->timeline) ctx->apiLog.push_back({name, t0, host_now_us() - ctx->timelineHost0});
     }
 };
 
@@ -308,6 +351,7 @@ int check_buffer(uvrt_ctx* ctx, uvrt_buffer what, void** ptr, size_t* bytes)
     case UVRT_BUF_COLOR: *ptr = ctx->dColor; *bytes = n * 36; return UVRT_OK;
     case UVRT_BUF_PAIRS: *ptr = ctx->dPairs; *bytes = (size_t)std::max(ctx->nPairs, 1) * 64; return UVRT_OK;
     case UVRT_BUF_WTRIS: *ptr = ctx->dWtris; *bytes = (size_t)ctx->nSlots * 64; return UVRT_OK;
+    case UVRT_BUF_MATRIX: *ptr = ctx->dMatrix; *bytes = (size_t)ctx->matrixRows * n * 4; return UVRT_OK;
     }
     return fail(ctx, UVRT_ERR_INVALID, "unknown buffer id %d", (int)what);
 }
@@ -337,6 +381,7 @@ void launch_simple_cfg(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
         ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm, 0, ctx->genericOctant);
 }
 
+#ifdef UVRT_EXPERIMENTS
 template <int K, int CH>
 void launch_chunk_kc(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
@@ -354,6 +399,8 @@ void launch_chunk_k(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     else if (ctx->chunk <= 256) launch_chunk_kc<K, 256>(ctx, nRays, perm);
     else launch_chunk_kc<K, 1024>(ctx, nRays, perm);
 }
+
+#endif
 
 template <int DIV>
 void launch_simple(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
@@ -373,15 +420,18 @@ void launch_simple_fetch(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
         cudaFuncSetAttribute(k_extend_simple<DIV_MARKSTEIN1, kStack, 128, 12, FETCH>, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->carveout);
     }
     unsigned int* cursor = nullptr;
+#ifdef UVRT_EXPERIMENTS
     if (FETCH == 5) {
         if (!ctx->dSmCursor) cudaMalloc((void**)&ctx->dSmCursor, 2 * 1024 * sizeof(unsigned int));
         cursor = ctx->dSmCursor + 1024 * ctx->slot;          // one cursor table per ray slot: extends may overlap
         cudaMemsetAsync(cursor, 0, 1024 * sizeof(unsigned int), ctx->xStream);
     }
+#endif
     k_extend_simple<DIV_MARKSTEIN1, kStack, 128, 12, FETCH><<<grid_for(nRays, 128), 128, 0, ctx->xStream>>>(
         ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->rootRef, nRays, ctx->sceneTame, perm, ctx->pairsTex, 0, cursor);
 }
 
+#ifdef UVRT_EXPERIMENTS
 template <int DIV, int K, int HIST, int REFILL>
 void launch_persist_r(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
@@ -424,10 +474,12 @@ void launch_persist_d(uvrt_ctx* ctx, long long nRays, int d, const uint32_t* per
     else launch_persist_h<DIV_MARKSTEIN1, K>(ctx, nRays, perm);
 }
 
+#endif
+
 // Counting sort of the ray queue (kernels: uvrt_kernels.cuh "ray binning").  bin_prepare sizes the
 // tables; the count step runs inside k_generate (countedRays) or as k_bin_count; bin_finish scans and
 // scatters, leaving the permutation in ctx->rs().dPerm.
-int bin_prepare(uvrt_ctx* ctx, long long nRays, BinDims* d)
+int bin_prepare(uvrt_ctx* ctx, long long nRays, BinDims* d, cudaStream_t stream)
 {
     const int wanted = ctx->binY * ctx->binT * ctx->binP;
     int nBins = kBinsPerScanBlock;
@@ -443,7 +495,9 @@ int bin_prepare(uvrt_ctx* ctx, long long nRays, BinDims* d)
         CK(cudaMalloc((void**)&ctx->rs().dBinCount, (size_t)nBins * 4));
         CK(cudaMalloc((void**)&ctx->rs().dBinStart, (size_t)nBins * 4));
         CK(cudaMalloc((void**)&ctx->rs().dBinBlock, 64 * 4));
-        CK(cudaMemset(ctx->rs().dBinCount, 0, (size_t)nBins * 4));   // rare: synchronous on purpose
+        // on the stream of the kernel that takes the bin slots next: a plain cudaMemset runs on the legacy stream,
+        // which nothing orders before the non-blocking streams of this context
+        CK(cudaMemsetAsync(ctx->rs().dBinCount, 0, (size_t)nBins * 4, stream));
         ctx->rs().binCap = nBins;
     }
     ctx->rs().binUsed = nBins;
@@ -469,7 +523,7 @@ int bin_finish(uvrt_ctx* ctx, long long nRays, cudaStream_t stream)
     if (ctx->rs().countedRays != nRays) {
         // the rays in the buffer did not (all) come from k_generate<1>: count them now
         BinDims d;
-        int rc = bin_prepare(ctx, nRays, &d);
+        int rc = bin_prepare(ctx, nRays, &d, stream);
         if (rc) return rc;
         if (ctx->rs().countedRays >= 0) CK(cudaMemsetAsync(ctx->rs().dBinCount, 0, (size_t)ctx->rs().binCap * 4, stream));
         k_bin_count<<<grid_for(nRays, 256), 256, 0, stream>>>(ctx->rs().dRays, (uint32_t)nRays, d, ctx->rs().dBinCount, ctx->rs().dKeyRank);
@@ -490,12 +544,15 @@ int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     int v = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
     if (v == 0) launch_simple<DIV_IEEE>(ctx, nRays, perm);
     else if (v == 1) launch_simple<DIV_MARKSTEIN2>(ctx, nRays, perm);
+    else if (v == 2 && ctx->fetchMode == 3 && ctx->simpleCfg == 1) launch_simple_fetch<3>(ctx, nRays, perm);
+#ifdef UVRT_EXPERIMENTS
     else if (v == 2 && ctx->fetchMode == 1 && ctx->pairsTex) launch_simple_fetch<1>(ctx, nRays, perm);
     else if (v == 2 && ctx->fetchMode == 2 && ctx->pairsTex) launch_simple_fetch<2>(ctx, nRays, perm);
-    else if (v == 2 && ctx->fetchMode == 3 && ctx->simpleCfg == 1) launch_simple_fetch<3>(ctx, nRays, perm);
     else if (v == 2 && ctx->fetchMode == 4) launch_simple_fetch<4>(ctx, nRays, perm);
     else if (v == 2 && ctx->fetchMode == 5 && perm) launch_simple_fetch<5>(ctx, nRays, perm);
+#endif
     else if (v == 2) launch_simple<DIV_MARKSTEIN1>(ctx, nRays, perm);
+#ifdef UVRT_EXPERIMENTS
     else if (v >= 40 && v < 44) {
         // chunk-persistent warps (k_extend_chunk): K = {1, 2, 4, 8}[v - 40]; "refill", "chunk" options
         switch (v - 40) {
@@ -514,8 +571,15 @@ int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
         case 3: launch_persist_d<8>(ctx, nRays, d, perm); break;
         default: launch_persist_d<16>(ctx, nRays, d, perm); break;
         }
-    } else
-        return fail(ctx, UVRT_ERR_INVALID, "unknown extend_variant %d", v);
+    }
+#endif
+    else
+        return fail(ctx, UVRT_ERR_INVALID, "unknown extend_variant %d%s", v,
+#ifdef UVRT_EXPERIMENTS
+                    "");
+#else
+                    " (variants 10..24 and 40..43 exist only in builds with -DUVRT_EXPERIMENTS)");
+#endif
     ctx->launches++;
     return UVRT_OK;
 }
@@ -614,6 +678,9 @@ void uvrt_destroy(uvrt_ctx* ctx)
     if (ctx->forkEv) cudaEventDestroy(ctx->forkEv);
     if (ctx->accStream) { cudaStreamSynchronize(ctx->accStream); cudaStreamDestroy(ctx->accStream); }
     if (ctx->dCountsAlt) cudaFree(ctx->dCountsAlt);
+    if (ctx->dMatrix) cudaFree(ctx->dMatrix);
+    if (ctx->dDurations) cudaFree(ctx->dDurations);
+    if (ctx->timelineOrigin) cudaEventDestroy(ctx->timelineOrigin);
     if (ctx->dVertsSpare) cudaFree(ctx->dVertsSpare);
     if (ctx->vertsEv) cudaEventDestroy(ctx->vertsEv);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
@@ -650,15 +717,42 @@ int uvrt_device_info(uvrt_ctx* ctx, char* dst, size_t bytes, int* smCount, int* 
     return UVRT_OK;
 }
 
-// device buffers of the traversal layout and the per-triangle state
-static int ensure_scene_buffers(uvrt_ctx* ctx, size_t pairBytes, size_t wtriBytes, int nTris)
+// device buffers of the traversal layout and the per-triangle state.  Everything the new scene needs is
+// allocated BEFORE anything of the old scene is released, so a failed allocation leaves the old scene usable
+// (the header's promise for rejected uploads).
+static int ensure_scene_buffers(uvrt_ctx* ctx, size_t pairBytes, size_t wtriBytes, int nTris, bool vertsToo)
 {
-    int rc;
-    if (pairBytes > ctx->pairCap) {
-        ctx->pairCap = 0;
+    float4 *nPairsBuf = nullptr, *nWtris = nullptr, *nVerts = nullptr;
+    int *nCounts = nullptr, *nCountsAlt = nullptr;
+    double *nSum = nullptr, *nMax = nullptr;
+    float *nDose = nullptr, *nColor = nullptr;
+    const bool growPairs = pairBytes > ctx->pairCap, growWtris = wtriBytes > ctx->wtriCap;
+    const bool growVerts = vertsToo && (size_t)nTris > ctx->vertsCap, perTri = nTris != ctx->nTris;
+    cudaError_t e = cudaSuccess;
+    auto want = [&](bool on, void** p, size_t bytes) { if (on && e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    want(growPairs, (void**)&nPairsBuf, pairBytes);
+    want(growWtris, (void**)&nWtris, wtriBytes);
+    want(growVerts, (void**)&nVerts, (size_t)nTris * 64);
+    want(perTri, (void**)&nCounts, (size_t)nTris * 4);
+    want(perTri, (void**)&nCountsAlt, (size_t)nTris * 4);
+    want(perTri, (void**)&nSum, (size_t)nTris * 8);
+    want(perTri, (void**)&nMax, (size_t)nTris * 8);
+    want(perTri, (void**)&nDose, (size_t)nTris * 4);
+    want(perTri, (void**)&nColor, (size_t)nTris * 36);
+    if (e != cudaSuccess) {
+        void* fresh[] = {nPairsBuf, nWtris, nVerts, nCounts, nCountsAlt, nSum, nMax, nDose, nColor};
+        for (void* p : fresh) if (p) cudaFree(p);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? UVRT_ERR_NO_MEMORY : UVRT_ERR_CUDA,
+                    "upload_scene: device allocation failed (%s); the previous scene is untouched", cudaGetErrorString(e));
+    }
+    auto swapIn = [](auto** slot, auto* fresh) { if (*slot) cudaFree(*slot); *slot = fresh; };
+    if (growPairs) {
+#ifdef UVRT_EXPERIMENTS
         if (ctx->pairsTex) { cudaDestroyTextureObject(ctx->pairsTex); ctx->pairsTex = 0; }
-        if ((rc = dev_alloc(ctx, &ctx->dPairs, pairBytes / 16))) return rc;
+#endif
+        swapIn(&ctx->dPairs, nPairsBuf);
         ctx->pairCap = pairBytes;
+#ifdef UVRT_EXPERIMENTS
         if (pairBytes / 16 <= (1u << 27)) {
             cudaResourceDesc rd{};
             rd.resType = cudaResourceTypeLinear;
@@ -669,25 +763,14 @@ static int ensure_scene_buffers(uvrt_ctx* ctx, size_t pairBytes, size_t wtriByte
             td.readMode = cudaReadModeElementType;
             if (cudaCreateTextureObject(&ctx->pairsTex, &rd, &td, nullptr) != cudaSuccess) { ctx->pairsTex = 0; cudaGetLastError(); }
         }
+#endif
     }
-    if (wtriBytes > ctx->wtriCap) {
-        ctx->wtriCap = 0;
-        if ((rc = dev_alloc(ctx, &ctx->dWtris, wtriBytes / 16))) return rc;
-        ctx->wtriCap = wtriBytes;
-    }
-    if ((size_t)nTris > ctx->vertsCap) {
-        ctx->vertsCap = 0;
-        if ((rc = dev_alloc(ctx, &ctx->dVerts, (size_t)nTris * 4))) return rc;
-        ctx->vertsCap = (size_t)nTris;
-    }
-    if (nTris != ctx->nTris) {
-        ctx->nTris = 0;
-        if ((rc = dev_alloc(ctx, &ctx->dCounts, (size_t)nTris))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->dCountsAlt, (size_t)nTris))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->dSum, (size_t)nTris))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->dMax, (size_t)nTris))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->dDose, (size_t)nTris))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->dColor, (size_t)nTris * 9))) return rc;
+    if (growWtris) { swapIn(&ctx->dWtris, nWtris); ctx->wtriCap = wtriBytes; }
+    if (growVerts) { swapIn(&ctx->dVerts, nVerts); ctx->vertsCap = (size_t)nTris; }
+    if (perTri) {
+        swapIn(&ctx->dCounts, nCounts); swapIn(&ctx->dCountsAlt, nCountsAlt);
+        swapIn(&ctx->dSum, nSum); swapIn(&ctx->dMax, nMax);
+        swapIn(&ctx->dDose, nDose); swapIn(&ctx->dColor, nColor);
         ctx->nTris = nTris;
         CK(cudaMemsetAsync(ctx->dCounts, 0, (size_t)nTris * 4, ctx->stream));
         CK(cudaMemsetAsync(ctx->dCountsAlt, 0, (size_t)nTris * 4, ctx->stream));
@@ -854,6 +937,12 @@ static int upload_scene_device(uvrt_ctx* ctx, const void* trisV, int nTris, cons
     phase("wait for the walk");
     CK_LAUNCH("scene walk");
     const Status s = *hSt;
+    // every early return below leaves the previous scene in place; the triangle DMA from the staging area
+    // must have landed before the caller may reuse it (uvrt_build_bvh, the next upload)
+    struct DmaGuard {
+        cudaStream_t s; bool armed;
+        ~DmaGuard() { if (armed) cudaStreamSynchronize(s); }
+    } dmaGuard{ctx->genStream, true};
     switch (s.err) {
     case PREP_OK: break;
     case PREP_NODE_RANGE:
@@ -871,12 +960,14 @@ static int upload_scene_device(uvrt_ctx* ctx, const void* trisV, int nTris, cons
     const int nPairs = (int)s.nPairs;
     const unsigned long long nSlots = s.nSlots;
     const size_t pairBytes = (size_t)std::max(nPairs, 1) * 64, wtriBytes = (size_t)std::max<unsigned long long>(nSlots, 1) * 64;
+    // the new scene's buffers first (an allocation failure must not cost the old scene its triangles), then the swap
+    if ((rc = ensure_scene_buffers(ctx, pairBytes, wtriBytes, nTris, false))) return rc;
     std::swap(ctx->dVerts, ctx->dVertsSpare);
     std::swap(ctx->vertsCap, ctx->vertsSpareCap);
-    if ((rc = ensure_scene_buffers(ctx, pairBytes, wtriBytes, nTris))) return rc;
+    dmaGuard.armed = false;
     CK(cudaStreamWaitEvent(st, ctx->vertsEv, 0));
     if (nPairs == 0) CK(cudaMemsetAsync(ctx->dPairs, 0, pairBytes, st));
-    const uint32_t reachable = s.tail;
+    const uint32_t reachable = std::min<uint32_t>(s.tail, (uint32_t)nNodes);
     k_prep_emit<<<grid_for(reachable, 256), 256, 0, st>>>((const RawNode*)ctx->dRawNodes, ctx->dRawIdx, ctx->dVerts, ctx->dPrepQueue,
                                                          reachable, parent, subInner, subSlots, ctx->dPairs, ctx->dWtris, dSt);
     CK(cudaMemcpyAsync(hSt, dSt, sizeof(Status), cudaMemcpyDeviceToHost, st));
@@ -999,7 +1090,7 @@ static int upload_scene_host(uvrt_ctx* ctx, const void* trisV, int nTris, const 
 
     // ---- device buffers -------------------------------------------------------------------------
     int rc;
-    if ((rc = ensure_scene_buffers(ctx, pairBytes, wtriBytes, nTris))) return rc;
+    if ((rc = ensure_scene_buffers(ctx, pairBytes, wtriBytes, nTris, true))) return rc;
     CK(cudaMemcpyAsync(ctx->dPairs, hp, pairBytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dWtris, hw, wtriBytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dVerts, hv, vertBytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -1020,6 +1111,7 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
     if (!ctx) return UVRT_ERR_INVALID;
     if (!trisV || !nodesV || !triIdx || nTris <= 0 || nNodes <= 0)
         return fail(ctx, UVRT_ERR_INVALID, "upload_scene: null pointer or empty scene (nTris=%d nNodes=%d)", nTris, nNodes);
+    ApiScope api_(ctx, "uvrt_upload_scene");
     Bind b(ctx);
     // rays of a pipelined launch may still be in flight on the second stream
     if (ctx->genStream) CK(cudaStreamSynchronize(ctx->genStream));
@@ -1035,6 +1127,7 @@ int uvrt_build_bvh(uvrt_ctx* ctx, const void* trisHost, int nTris, void* nodesOu
     if (!ctx) return UVRT_ERR_INVALID;
     if (!trisHost || nTris <= 0 || !nodesOut || !triIdxOut)
         return fail(ctx, UVRT_ERR_INVALID, "build_bvh: null pointer or empty mesh");
+    ApiScope api_(ctx, "uvrt_build_bvh");
     Bind b(ctx);
     const bool verbose = getenv("UVRT_BVH_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1204,6 +1297,7 @@ int uvrt_scene_info(uvrt_ctx* ctx, int* innerNodes, int* leaves, int* depth, int
 #define NEED_SCENE()                                                                       \
     if (!ctx) return UVRT_ERR_INVALID;                                                     \
     if (!ctx->nTris) return fail(ctx, UVRT_ERR_NO_SCENE, "%s: no scene uploaded", __func__); \
+    ApiScope api_(ctx, __func__);                                                          \
     Bind bind_(ctx)
 
 int uvrt_reset(uvrt_ctx* ctx, int resetColor)
@@ -1243,7 +1337,7 @@ static int generate_on(uvrt_ctx* ctx, cudaStream_t stream, float lx, float ly, f
     if (nRays == 0) return UVRT_OK;
     if (wants_binning(ctx, nRays)) {
         BinDims d;
-        rc = bin_prepare(ctx, nRays, &d);
+        rc = bin_prepare(ctx, nRays, &d, stream);
         if (rc) return rc;
         StageTimer t(ctx, UVRT_STAGE_GENERATE, stream);
         k_generate<1><<<grid_for(nRays, 256), 256, 0, stream>>>(S.dRays, firstRay, nRays, lx, ly, lz, lightLength, seedIn,
@@ -1351,6 +1445,7 @@ int uvrt_trace(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, f
 {
     if (!ctx) return UVRT_ERR_INVALID;
     if (!ctx->nTris) return fail(ctx, UVRT_ERR_NO_SCENE, "%s: no scene uploaded", __func__);
+    ApiScope api_(ctx, "uvrt_trace");
     const bool foreign = ctx->mainForeign;
     const int variant = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
     const bool sharedQueue = variant >= 10 && variant < 25;   // variant B's global queue head is one per context
@@ -1424,12 +1519,148 @@ int uvrt_trace(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, f
     return UVRT_OK;
 }
 
+// ---- count matrix: launches of a run write their integer counts to one row each -----------------------
+// For runs whose launches are shared between GPUs (whole launches or ray ranges of a launch): every rank
+// traces its rays of launch k into row k, ONE all-reduce sums the integer rows, and the fold replays
+// accumulate.cl:4-14 row by row in launch order on every rank -- the f64 sums and the per-launch maxima are
+// then bit-identical to the single-GPU run for ANY split and ANY durations.
+int uvrt_matrix_begin(uvrt_ctx* ctx, int rows)
+{
+    NEED_SCENE();
+    if (rows < 1) return fail(ctx, UVRT_ERR_INVALID, "matrix_begin: rows = %d", rows);
+    const size_t need = (size_t)rows * (size_t)ctx->nTris;
+    if (need > ctx->matrixCap) {
+        int* fresh = nullptr;
+        CK(cudaMalloc((void**)&fresh, need * 4));
+        if (ctx->dMatrix) cudaFree(ctx->dMatrix);
+        ctx->dMatrix = fresh;
+        ctx->matrixCap = need;
+    }
+    if (rows > ctx->durCap) {
+        float* fresh = nullptr;
+        CK(cudaMalloc((void**)&fresh, (size_t)rows * 4));
+        if (ctx->dDurations) cudaFree(ctx->dDurations);
+        ctx->dDurations = fresh;
+        ctx->durCap = rows;
+    }
+    // the rows of the previous window may still be read by its fold on the main stream: same stream, in order
+    CK(cudaMemsetAsync(ctx->dMatrix, 0, need * 4, ctx->stream));
+    ctx->matrixRows = rows;
+    return UVRT_OK;
+}
+
+int uvrt_trace_row(uvrt_ctx* ctx, int row, float lx, float ly, float lz, float lightLength, int64_t firstRay, int64_t nRays,
+                   uint32_t seedIn)
+{
+    if (!ctx) return UVRT_ERR_INVALID;
+    if (!ctx->nTris) return fail(ctx, UVRT_ERR_NO_SCENE, "%s: no scene uploaded", __func__);
+    if (row < 0 || row >= ctx->matrixRows) return fail(ctx, UVRT_ERR_INVALID, "trace_row: row %d outside the matrix (%d rows)", row, ctx->matrixRows);
+    if (nRays <= 0) return nRays == 0 ? UVRT_OK : fail(ctx, UVRT_ERR_INVALID, "trace_row: nRays = %lld", (long long)nRays);
+    ApiScope api_(ctx, "uvrt_trace_row");
+    const bool foreign = ctx->mainForeign;
+    Bind b(ctx);
+    // the stream choreography of the overlapped uvrt_trace without its accumulates: generate + bin on the
+    // generate stream, extend on the ray slot's own stream; rows are disjoint, so extends never wait for each other
+    ctx->slot ^= 1;
+    const int si = ctx->slot;
+    RaySlot& S = ctx->rs();
+    cudaStream_t es = ctx->extStream[si];
+    if (foreign) {
+        CK(cudaEventRecord(ctx->forkEv, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->extStream[0], ctx->forkEv, 0));
+        CK(cudaStreamWaitEvent(ctx->extStream[1], ctx->forkEv, 0));
+        CK(cudaStreamWaitEvent(ctx->accStream, ctx->forkEv, 0));
+        CK(cudaStreamWaitEvent(ctx->genStream, ctx->forkEv, 0));
+    }
+    if (S.inFlight) CK(cudaStreamWaitEvent(ctx->genStream, S.freeEv, 0));
+    int rc = generate_on(ctx, ctx->genStream, lx, ly, lz, lightLength, firstRay, nRays, seedIn);
+    if (rc) return rc;
+    const uint32_t* perm = nullptr;
+    if (wants_binning(ctx, nRays)) {
+        rc = bin_finish(ctx, nRays, ctx->genStream);
+        if (rc) return rc;
+        CK_LAUNCH("bin");
+        perm = S.dPerm;
+    }
+    CK(cudaEventRecord(S.genDone, ctx->genStream));
+    CK(cudaStreamWaitEvent(es, S.genDone, 0));
+    ctx->xStream = es;
+    ctx->xCounts = ctx->dMatrix + (size_t)row * (size_t)ctx->nTris;
+    {
+        StageTimer t(ctx, UVRT_STAGE_EXTEND, es);
+        rc = launch_extend(ctx, nRays, perm);
+    }
+    ctx->xStream = ctx->stream;
+    ctx->xCounts = ctx->dCounts;
+    if (rc) return rc;
+    CK_LAUNCH("extend");
+    CK(cudaEventRecord(ctx->extDone[si], es));
+    CK(cudaEventRecord(S.freeEv, es));
+    S.inFlight = true;
+    ctx->extUsed[si] = true;
+    ctx->mainForeign = false;
+    return UVRT_OK;
+}
+
+int uvrt_matrix_fold(uvrt_ctx* ctx, const float* durations, int rows, int reduce)
+{
+    NEED_SCENE();
+    if (rows < 0 || rows > ctx->matrixRows || (rows > 0 && !durations))
+        return fail(ctx, UVRT_ERR_INVALID, "matrix_fold: rows = %d of %d", rows, ctx->matrixRows);
+    for (int k = 0; k < 2; k++)
+        if (ctx->extUsed[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->extDone[k], 0));
+    if (rows == 0) return UVRT_OK;
+    if (reduce && (ctx->nRanks > 1 || ctx->comm)) {
+        if (!ctx->comm) return fail(ctx, UVRT_ERR_NCCL, "matrix_fold: uvrt_comm_init was not called");
+        nvtxRangePushA("ncclAllReduce(count matrix)");
+        int r = g_nccl.AllReduce(ctx->dMatrix, ctx->dMatrix, (size_t)rows * (size_t)ctx->nTris, kNcclInt32, kNcclSum, ctx->comm, ctx->stream);
+        nvtxRangePop();
+        if (r != kNcclSuccess) return fail(ctx, UVRT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+    }
+    CK(cudaMemcpyAsync(ctx->dDurations, durations, (size_t)rows * 4, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        StageTimer t(ctx, UVRT_STAGE_ACCUMULATE);
+        k_fold_rows<<<grid_for(ctx->nTris, 256), 256, 0, ctx->stream>>>(ctx->dSum, ctx->dMax, ctx->dMatrix, ctx->dDurations, rows, ctx->nTris);
+    }
+    ctx->launches++;
+    CK_LAUNCH("fold");
+    return UVRT_OK;
+}
+
+// ---- timeline ("timeline" option): where the wall clock of a run goes ------------------------------------
+int uvrt_timeline_dump(uvrt_ctx* ctx, const char* path)
+{
+    if (!ctx || !path) return UVRT_ERR_INVALID;
+    Bind b(ctx);
+    CK(uvrt_sync(ctx) == UVRT_OK ? cudaSuccess : cudaErrorUnknown);
+    FILE* f = fopen(path, "w");
+    if (!f) return fail(ctx, UVRT_ERR_IO, "timeline_dump: cannot write %s", path);
+    fprintf(f, "{\"unit\": \"us since the option was switched on (host clock for calls, device clock for kernels)\",\n \"calls\": [");
+    for (size_t i = 0; i < ctx->apiLog.size(); i++)
+        fprintf(f, "%s[\"%s\", %.1f, %.1f]", i ? ", " : "", ctx->apiLog[i].name, ctx->apiLog[i].t0, ctx->apiLog[i].t1);
+    fprintf(f, "],\n \"kernels\": [");
+    bool first = true;
+    for (size_t i = 0; i < ctx->timed.size() && i < ctx->timedHost.size(); i++) {
+        float a = 0, z = 0;
+        if (!ctx->timelineOrigin || cudaEventElapsedTime(&a, ctx->timelineOrigin, ctx->timed[i].start) != cudaSuccess ||
+            cudaEventElapsedTime(&z, ctx->timelineOrigin, ctx->timed[i].stop) != cudaSuccess) { cudaGetLastError(); continue; }
+        const int st = ctx->timed[i].stage;
+        fprintf(f, "%s[\"%s\", %.1f, %.1f, %.1f]", first ? "" : ", ", st >= 0 && st < UVRT_STAGE_COUNT ? kStageNames[st] : "?", ctx->timedHost[i],
+                a * 1e3, z * 1e3);
+        first = false;
+    }
+    fprintf(f, "]}\n");
+    fclose(f);
+    return UVRT_OK;
+}
+
 int uvrt_seed_chain(uvrt_ctx* ctx, const float* lightPos3, int nLaunches, float lightLength, uint32_t seedIn,
                     uint32_t* seedsOut)
 {
     if (!ctx) return UVRT_ERR_INVALID;
     if (nLaunches < 0 || !seedsOut || (nLaunches > 0 && !lightPos3))
         return fail(ctx, UVRT_ERR_INVALID, "seed_chain: bad arguments");
+    ApiScope api_(ctx, "uvrt_seed_chain");
     Bind b(ctx);
     if (nLaunches + 1 > ctx->seedCap) {
         int cap = std::max(nLaunches + 1, 256);
@@ -1483,6 +1714,9 @@ int uvrt_read(uvrt_ctx* ctx, uvrt_buffer what, void* dst, size_t bytes)
     int rc = check_buffer(ctx, what, &p, &cap);
     if (rc) return rc;
     if (!dst || bytes > cap) return fail(ctx, UVRT_ERR_INVALID, "read: %zu bytes requested, buffer %d holds %zu", bytes, (int)what, cap);
+    if (what == UVRT_BUF_MATRIX)      // rows are written by the extend streams of uvrt_trace_row
+        for (int k = 0; k < 2; k++)
+            if (ctx->extUsed[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->extDone[k], 0));
     if (bytes) CK(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return UVRT_OK;
@@ -1508,6 +1742,9 @@ int uvrt_write(uvrt_ctx* ctx, uvrt_buffer what, const void* src, size_t bytes)
     int rc = check_buffer(ctx, what, &p, &cap);
     if (rc) return rc;
     if (!src || bytes > cap) return fail(ctx, UVRT_ERR_INVALID, "write: %zu bytes offered, buffer %d holds %zu", bytes, (int)what, cap);
+    if (what == UVRT_BUF_MATRIX)
+        for (int k = 0; k < 2; k++)
+            if (ctx->extUsed[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->extDone[k], 0));
     if (bytes) CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (what == UVRT_BUF_COUNTS) ctx->countsDirty = true;
@@ -1517,6 +1754,7 @@ int uvrt_write(uvrt_ctx* ctx, uvrt_buffer what, const void* src, size_t bytes)
 int uvrt_sync(uvrt_ctx* ctx)
 {
     if (!ctx) return UVRT_ERR_INVALID;
+    ApiScope api_(ctx, "uvrt_sync");
     Bind b(ctx);
     CK(cudaStreamSynchronize(ctx->genStream));
     CK(cudaStreamSynchronize(ctx->extStream[0]));
@@ -1584,6 +1822,20 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
     if (!ctx || !key) return UVRT_ERR_INVALID;
     if (!strcmp(key, "extend_variant")) ctx->extendVariant = value;
     else if (!strcmp(key, "stage_timing")) ctx->stageTiming = value;
+    else if (!strcmp(key, "timeline")) {
+        Bind b(ctx);
+        uvrt_stage_time_reset(ctx);
+        ctx->apiLog.clear();
+        ctx->timedHost.clear();
+        ctx->timeline = value;
+        if (value) {
+            if (!ctx->timelineOrigin) CK(cudaEventCreate(&ctx->timelineOrigin));
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaEventRecord(ctx->timelineOrigin, ctx->stream));
+            CK(cudaEventSynchronize(ctx->timelineOrigin));
+            ctx->timelineHost0 = host_now_us();
+        }
+    }
     else if (!strcmp(key, "hist_mode")) ctx->histMode = value;
     else if (!strcmp(key, "blocks_per_sm")) ctx->blocksPerSm = value;
     else if (!strcmp(key, "refill")) ctx->refill = value;
@@ -1617,9 +1869,17 @@ int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value)
     if (!ctx || !key || !value) return UVRT_ERR_INVALID;
     if (!strcmp(key, "extend_variant")) *value = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
     else if (!strcmp(key, "stage_timing")) *value = ctx->stageTiming;
+    else if (!strcmp(key, "timeline")) *value = ctx->timeline;
     else if (!strcmp(key, "hist_mode")) *value = ctx->histMode;
     else if (!strcmp(key, "blocks_per_sm")) *value = ctx->blocksPerSm;
     else if (!strcmp(key, "scene_tame")) *value = ctx->sceneTame;
+    else if (!strcmp(key, "experiments")) {
+#ifdef UVRT_EXPERIMENTS
+        *value = 1;
+#else
+        *value = 0;
+#endif
+    }
     else if (!strcmp(key, "refill")) *value = ctx->refill;
     else if (!strcmp(key, "simple_cfg")) *value = ctx->simpleCfg;
     else if (!strcmp(key, "generic_octant")) *value = ctx->genericOctant;
@@ -1672,6 +1932,7 @@ int uvrt_stage_time_reset(uvrt_ctx* ctx)
     CK(cudaStreamSynchronize(ctx->stream));
     for (auto& t : ctx->timed) { ctx->freeEvents.push_back(t.start); ctx->freeEvents.push_back(t.stop); }
     ctx->timed.clear();
+    ctx->timedHost.clear();
     return UVRT_OK;
 }
 
@@ -1693,6 +1954,9 @@ int uvrt_mark(uvrt_ctx* ctx, int slot)
 {
     if (!ctx || slot < 0 || slot >= 16) return UVRT_ERR_INVALID;
     Bind b(ctx);
+    // rows of a count matrix are still being written on the extend streams (uvrt_trace_row): a mark covers them
+    for (int k = 0; k < 2; k++)
+        if (ctx->extUsed[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->extDone[k], 0));
     CK(cudaEventRecord(ctx->marks[slot], ctx->stream));
     // work of later calls on the second stream must not start before the mark
     CK(cudaStreamWaitEvent(ctx->genStream, ctx->marks[slot], 0));

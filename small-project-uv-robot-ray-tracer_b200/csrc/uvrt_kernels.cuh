@@ -46,14 +46,16 @@ __device__ __forceinline__ W4 ldg256w(const float4* p)
     asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w0), "=l"(r.w1), "=l"(r.w2), "=l"(r.w3) : "l"(p));
     return r;
 }
-// cache-hint experiments ("fetch_mode" 3/4): nodes marked evict_last in L1, streaming data (rays,
-// permutation, results) kept out of L1
+#ifdef UVRT_EXPERIMENTS
+// cache-hint experiment ("fetch_mode" 4): nodes marked evict_last in L1
 __device__ __forceinline__ W4 ldg256w_keep(const float4* p)
 {
     W4 r;
     asm("ld.global.nc.L1::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.w0), "=l"(r.w1), "=l"(r.w2), "=l"(r.w3) : "l"(p));
     return r;
 }
+#endif
+// streaming data (rays, permutation, results) is kept out of L1 ("fetch_mode" 3, the default)
 __device__ __forceinline__ F8 ld256_stream(const float4* p)
 {
     F8 r;
@@ -447,8 +449,9 @@ __device__ __forceinline__ bool ray_is_tame(const RayCtx& r)
 // reference's.  `pairs` holds, per inner node, its two children's boxes and references
 // (2 x 32 bytes, see intersect_aabb); `wtris` holds leaf triangles in leaf order (4 x float4:
 // v0+tag, edge1, edge2, pad -- two 32-byte sectors).
-// Node fetch path (experiment, "fetch_mode"): 0 = two LDG.256 through the LSU; 1 = four 16-byte
-// texture fetches; 2 = first child through the LSU, second through the texture unit.
+// Node fetch path: two LDG.256 through the LSU.  (UVRT_EXPERIMENTS builds also know "fetch_mode" 1 = four
+// 16-byte texture fetches, 2 = second child through the texture unit, 4 = evict_last: all measured slower.)
+#ifdef UVRT_EXPERIMENTS
 __device__ __forceinline__ W4 tex_w4(cudaTextureObject_t tex, uint32_t texel)
 {
     float4 a = tex1Dfetch<float4>(tex, (int)texel), b = tex1Dfetch<float4>(tex, (int)texel + 1);
@@ -456,6 +459,7 @@ __device__ __forceinline__ W4 tex_w4(cudaTextureObject_t tex, uint32_t texel)
     r.w0 = pk2(a.x, a.y); r.w1 = pk2(a.z, a.w); r.w2 = pk2(b.x, b.y); r.w3 = pk2(b.z, b.w);
     return r;
 }
+#endif
 
 template <int DIV, int STACK, int OCT, int FETCH = 0>
 __device__ __forceinline__ void bvh_intersect(RayCtx& ray, const float4* __restrict__ pairs,
@@ -485,10 +489,13 @@ __device__ __forceinline__ void bvh_intersect(RayCtx& ray, const float4* __restr
         }
         const float4* p = pairs + 4ull * cur;
         W4 ca, cb;
+#ifdef UVRT_EXPERIMENTS
         if (FETCH == 1) { ca = tex_w4(tex, cur * 4u); cb = tex_w4(tex, cur * 4u + 2u); }
         else if (FETCH == 2) { ca = ldg256w(p); cb = tex_w4(tex, cur * 4u + 2u); }
         else if (FETCH == 4) { ca = ldg256w_keep(p); cb = ldg256w_keep(p + 2); }
-        else { ca = ldg256w(p); cb = ldg256w(p + 2); }
+        else
+#endif
+        { ca = ldg256w(p); cb = ldg256w(p + 2); }
         float t1, t2;
         const bool h1 = intersect_aabb<DIV, OCT>(ray, ca, t1);
         const bool h2 = intersect_aabb<DIV, OCT>(ray, cb, t2);
@@ -562,6 +569,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_extend_simple(int* __res
                                                        int genericOctant = 0, unsigned int* __restrict__ smCursor = nullptr)
 {
     long long i;
+#ifdef UVRT_EXPERIMENTS
     if (FETCH == 5) {
         // SM-affine chunks ("fetch_mode 5"): the binned ray order is cut into one contiguous range per SM
         // and a block takes the next 128-ray chunk of the range of the SM it happens to run on, so the
@@ -589,6 +597,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_extend_simple(int* __res
         if (sChunk == 0xffffffffu) return;
         i = (long long)sChunk * blockDim.x + threadIdx.x;
     } else
+#endif
         i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nRays) return;
     if (perm) i = FETCH >= 3 ? ldg_u32_stream(perm + i) : perm[i];
@@ -607,233 +616,11 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_extend_simple(int* __res
     if (ray.dist != kNoHit) atomicAdd(&counts[ray.tri], 1);
 }
 
-// Variant B: persistent warps that pull rays from a global queue.  Lanes whose ray has finished
-// are refilled together (one warp-aggregated atomicAdd on the queue head per refill) once fewer
-// than REFILL lanes are still busy, so a warp is not held hostage by its longest ray.  Inside,
-// every lane alternates between at most K inner-node steps and one leaf visit; the per-ray
-// sequence of box tests, triangle tests and distance updates is exactly variant A's.
-// HIST = 1 counts hits in a shared-memory table first (block-level pre-reduction of hot triangle
-// IDs) and only spills colliding IDs and the final table to the global counters.
-template <int HBITS>
-struct HitTable {
-    uint32_t tag[1 << HBITS];
-    int cnt[1 << HBITS];
-};
-
-template <int HBITS>
-__device__ __forceinline__ void hist_add(HitTable<HBITS>* tab, int* __restrict__ counts, uint32_t tri)
-{
-    uint32_t slot = (tri * 2654435761u) >> (32 - HBITS);
-    uint32_t old = atomicCAS(&tab->tag[slot], 0xffffffffu, tri);
-    if (old == 0xffffffffu || old == tri) atomicAdd(&tab->cnt[slot], 1);
-    else atomicAdd(&counts[tri], 1);
-}
-
-template <int DIV, int STACK, int K, int REFILL, int HIST, int THREADS, int MINBLOCKS>
-__global__ void __launch_bounds__(THREADS, MINBLOCKS)
-k_extend_persist(int* __restrict__ counts, const float4* __restrict__ wtris, float4* __restrict__ rays,
-                 const float4* __restrict__ pairs, uint32_t rootRef, uint32_t nRays, int sceneTame,
-                 unsigned int* __restrict__ queueHead, const uint32_t* __restrict__ perm)
-{
-    constexpr int HBITS = 11;
-    __shared__ HitTable<HIST ? HBITS : 1> tab;
-    if (HIST) {
-        for (int i = threadIdx.x; i < (1 << HBITS); i += THREADS) { tab.tag[i] = 0xffffffffu; tab.cnt[i] = 0; }
-        __syncthreads();
-    }
-    uint32_t stack[STACK];
-    const unsigned lane = threadIdx.x & 31u;
-    RayCtx ray;
-    ray.ox = ray.oy = ray.oz = ray.dx = ray.dy = ray.dz = 0.0f;
-    ray.noXY = ray.noZZ = ray.rXY = ray.rZZ = ray.ndXY = ray.ndZZ = 0ull;
-    ray.dist = kNoHit; ray.tri = 0;
-    uint32_t cur = 0, rayIdx = 0xffffffffu;
-    int sp = 0;
-    bool busy = false, tame = false, drained = false;
-
-    for (;;) {
-        // ---- refill (warp-converged) ----
-        unsigned idle = __ballot_sync(0xffffffffu, !busy);
-        if (idle && !drained) {
-            int leader = __ffs(idle) - 1;
-            unsigned cnt = __popc(idle);
-            unsigned base = 0;
-            if ((int)lane == leader) base = atomicAdd(queueHead, cnt);
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (!busy) {
-                unsigned idx = base + __popc(idle & ((1u << lane) - 1u));
-                if (base < nRays && idx < nRays) {
-                    rayIdx = perm ? perm[idx] : idx;
-                    load_ray(rays, rayIdx, ray);
-                    tame = false;
-                    if (DIV != DIV_IEEE && sceneTame && ray_is_tame(ray)) {
-                        tame = true;
-                        make_tame(ray);
-                    }
-                    cur = rootRef; sp = 0; busy = true;
-                }
-            }
-            // base is warp-uniform: once the queue is past the end nobody asks again
-            if (base >= nRays || nRays - base < cnt) drained = true;
-        }
-        unsigned act = __ballot_sync(0xffffffffu, busy);
-        if (act == 0u) break;
-
-        // ---- traverse until too few lanes are busy ----
-        for (;;) {
-#pragma unroll 1
-            for (int k = 0; k < K && busy && !(cur & kLeafFlag); k++) {
-                const float4* p = pairs + 4ull * cur;
-                W4 ca = ldg256w(p), cb = ldg256w(p + 2);
-                float t1, t2;
-                bool h1, h2;
-                if (DIV == DIV_IEEE || !tame) {
-                    h1 = intersect_aabb<DIV_IEEE, -1>(ray, ca, t1);
-                    h2 = intersect_aabb<DIV_IEEE, -1>(ray, cb, t2);
-                } else {
-                    h1 = intersect_aabb<DIV, -1>(ray, ca, t1);
-                    h2 = intersect_aabb<DIV, -1>(ray, cb, t2);
-                }
-                uint32_t first, second;
-                bool pushSecond;
-                if (order_children(h1, h2, t1, t2, child_ref(ca), child_ref(cb), first, second, pushSecond)) {
-                    cur = first;
-                    if (pushSecond) stack[sp++] = second;
-                } else {
-                    if (sp == 0) busy = false; else cur = stack[--sp];
-                }
-            }
-            if (busy && (cur & kLeafFlag)) {
-                uint32_t slot = cur & ~kLeafFlag;
-                uint32_t w;
-                do {
-                    const float4* t = wtris + 4ull * slot;
-                    F8 ta = ldg256(t), tb = ldg256(t + 2);
-                    w = __float_as_uint(ta.lo.w);
-                    intersect_tri(ray, ta.lo, ta.hi, tb.lo);
-                    slot++;
-                } while (!(w & kLastFlag));
-                if (sp == 0) busy = false; else cur = stack[--sp];
-            }
-            if (!busy && rayIdx != 0xffffffffu) {
-                // the ray just finished: write back (extend.cl:26 writes in place) and count
-                store_hit(rays, rayIdx, ray);
-                if (ray.dist != kNoHit) {
-                    if (HIST) hist_add<HBITS>(reinterpret_cast<HitTable<HBITS>*>(&tab), counts, ray.tri);
-                    else atomicAdd(&counts[ray.tri], 1);
-                }
-                rayIdx = 0xffffffffu;
-            }
-            act = __ballot_sync(0xffffffffu, busy);
-            if (act == 0u) break;
-            if (!drained && __popc(act) < REFILL) break;
-        }
-    }
-    if (HIST) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < (1 << HBITS); i += THREADS) {
-            int c = tab.cnt[i];
-            if (c) atomicAdd(&counts[tab.tag[i]], c);
-        }
-    }
-}
-
-
-// Variant C: persistent warps over PRIVATE chunks of the (binned) ray order.  Warp w owns rays
-// [w*CH, (w+1)*CH) of the permutation; lanes whose ray has finished are refilled from the warp's own
-// chunk (a warp-uniform cursor, no atomics) once fewer than `refill` lanes are busy.  Unlike variant B's
-// global queue this keeps the rays of a warp neighbours in the binned order, so the coherence the
-// binning created survives the refill; the tail where a warp waits for its longest ray is paid once per
-// CH rays instead of once per 32.  Per-ray test sequence as in variant A.
-template <int DIV, int STACK, int K, int CH, int THREADS, int MINBLOCKS>
-__global__ void __launch_bounds__(THREADS, MINBLOCKS)
-k_extend_chunk(int* __restrict__ counts, const float4* __restrict__ wtris, float4* __restrict__ rays,
-               const float4* __restrict__ pairs, uint32_t rootRef, uint32_t nRays, int sceneTame,
-               const uint32_t* __restrict__ perm, int refill)
-{
-    uint32_t stack[STACK];
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t warp = (blockIdx.x * THREADS + threadIdx.x) >> 5;
-    uint32_t next = warp * (uint32_t)CH;
-    const uint32_t end = min(next + (uint32_t)CH, nRays);
-    if (next >= nRays) return;
-    RayCtx ray;
-    ray.ox = ray.oy = ray.oz = ray.dx = ray.dy = ray.dz = 0.0f;
-    ray.noXY = ray.noZZ = ray.rXY = ray.rZZ = ray.ndXY = ray.ndZZ = 0ull;
-    ray.dist = kNoHit; ray.tri = 0;
-    uint32_t cur = 0, rayIdx = 0xffffffffu;
-    int sp = 0;
-    bool busy = false, tame = false;
-
-    for (;;) {
-        // ---- refill from the warp's own chunk (warp-converged) ----
-        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
-        if (idle && next < end) {
-            if (!busy) {
-                const uint32_t idx = next + __popc(idle & ((1u << lane) - 1u));
-                if (idx < end) {
-                    rayIdx = perm ? perm[idx] : idx;
-                    load_ray(rays, rayIdx, ray);
-                    tame = false;
-                    if (DIV != DIV_IEEE && sceneTame && ray_is_tame(ray)) {
-                        tame = true;
-                        make_tame(ray);
-                    }
-                    cur = rootRef; sp = 0; busy = true;
-                }
-            }
-            next = min(next + (uint32_t)__popc(idle), end);
-        }
-        unsigned act = __ballot_sync(0xffffffffu, busy);
-        if (act == 0u) break;
-
-        // ---- traverse until too few lanes are busy ----
-        for (;;) {
-#pragma unroll 1
-            for (int k = 0; k < K && busy && !(cur & kLeafFlag); k++) {
-                const float4* p = pairs + 4ull * cur;
-                W4 ca = ldg256w(p), cb = ldg256w(p + 2);
-                float t1, t2;
-                bool h1, h2;
-                if (DIV == DIV_IEEE || !tame) {
-                    h1 = intersect_aabb<DIV_IEEE, -1>(ray, ca, t1);
-                    h2 = intersect_aabb<DIV_IEEE, -1>(ray, cb, t2);
-                } else {
-                    h1 = intersect_aabb<DIV, -1>(ray, ca, t1);
-                    h2 = intersect_aabb<DIV, -1>(ray, cb, t2);
-                }
-                uint32_t first, second;
-                bool pushSecond;
-                if (order_children(h1, h2, t1, t2, child_ref(ca), child_ref(cb), first, second, pushSecond)) {
-                    cur = first;
-                    if (pushSecond) stack[sp++] = second;
-                } else {
-                    if (sp == 0) busy = false; else cur = stack[--sp];
-                }
-            }
-            if (busy && (cur & kLeafFlag)) {
-                uint32_t slot = cur & ~kLeafFlag;
-                uint32_t w;
-                do {
-                    const float4* t = wtris + 4ull * slot;
-                    F8 ta = ldg256(t), tb = ldg256(t + 2);
-                    w = __float_as_uint(ta.lo.w);
-                    intersect_tri(ray, ta.lo, ta.hi, tb.lo);
-                    slot++;
-                } while (!(w & kLastFlag));
-                if (sp == 0) busy = false; else cur = stack[--sp];
-            }
-            if (!busy && rayIdx != 0xffffffffu) {
-                store_hit(rays, rayIdx, ray);
-                if (ray.dist != kNoHit) atomicAdd(&counts[ray.tri], 1);
-                rayIdx = 0xffffffffu;
-            }
-            act = __ballot_sync(0xffffffffu, busy);
-            if (act == 0u) break;
-            if (next < end && (int)__popc(act) < refill) break;
-        }
-    }
-}
+#ifdef UVRT_EXPERIMENTS
+} // namespace uvrt
+#include "uvrt_experiments.cuh"   // rejected variants B / C (persistent warps), kept for A/B runs only
+namespace uvrt {
+#endif
 
 // ---- per-triangle passes ------------------------------------------------------------------
 // accumulate.cl:4-14
@@ -847,6 +634,23 @@ __global__ void __launch_bounds__(256) k_accumulate(double* __restrict__ photonM
     double m = maxPhotonMap[i];
     maxPhotonMap[i] = m < c ? c : m;
     temp[i] = 0;
+}
+
+// accumulate.cl:4-14 replayed over the rows of a count matrix (one row per launch, in launch order): the same
+// sequence of f64 operations per triangle as `rows` consecutive k_accumulate launches
+__global__ void __launch_bounds__(256) k_fold_rows(double* __restrict__ photonMap, double* __restrict__ maxPhotonMap,
+                                                   const int* __restrict__ matrix, const float* __restrict__ timeStep, int rows, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double sum = photonMap[i], m = maxPhotonMap[i];
+    for (int r = 0; r < rows; r++) {
+        const double c = (double)matrix[(size_t)r * (size_t)n + i];
+        sum = __dadd_rn(sum, __dmul_rn(c, (double)timeStep[r]));
+        m = m < c ? c : m;
+    }
+    photonMap[i] = sum;
+    maxPhotonMap[i] = m;
 }
 
 // shade.cl:23-41; `verts` is the reference-layout triangle array (64 B per triangle)

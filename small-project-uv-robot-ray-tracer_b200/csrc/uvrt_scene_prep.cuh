@@ -87,14 +87,16 @@ __global__ void __launch_bounds__(128) k_prep_walk(const RawNode* __restrict__ n
             const uint32_t c0 = nd.leftFirst, c1 = nd.leftFirst + 1;
             if (c1 >= nNodes || c1 < c0) { set_error(st, PREP_NODE_RANGE, c1 < c0 ? c0 : (c0 >= nNodes ? c0 : c1), 0, 0); return; }
             if ((int)depth + 1 >= maxDepth) { set_error(st, PREP_DEPTH, depth + 1, 0, 0); return; }
-            // three independent atomics in flight together (the level-to-level latency of this walk is what
-            // the upload waits for); queue slots reserved by a node that then fails stay empty, and `done`
-            // releases whoever waits for them
+            // The two claims travel together (the level-to-level latency of this walk is what the upload waits
+            // for); queue slots are reserved only by a node that owns both children, so `tail` never exceeds
+            // the number of distinct claimed nodes + 1 <= nNodes even on a malformed (DAG / cyclic) array --
+            // the validator must not write out of bounds on exactly the input it exists to reject.
             const uint32_t old0 = atomicCAS(&parent[c0], kNone, n);
             const uint32_t old1 = atomicCAS(&parent[c1], kNone, n);
-            const uint32_t pos = atomicAdd(&st->tail, 2u);
             if (old0 != kNone) { set_error(st, PREP_TWICE, c0, 0, 0); return; }
             if (old1 != kNone) { set_error(st, PREP_TWICE, c1, 0, 0); return; }
+            const uint32_t pos = atomicAdd(&st->tail, 2u);
+            if (pos + 1u >= nNodes) { set_error(st, PREP_NODE_RANGE, c1, 0, 0); return; }   // cannot happen for claimed pairs; belt and braces
             __threadfence();
             const unsigned long long d1 = (unsigned long long)(depth + 1) << 32;
             vq[pos] = d1 | c0;

@@ -5,6 +5,7 @@
 #include "precomp.h"
 #include "xml_min.h"
 #include "../../include/uvrt.h"
+#include <cstdio>
 #include <fstream>
 #include <sstream>
 
@@ -51,8 +52,7 @@ void RayTracer::Init(Mesh* m)
     }
     seedState = 0;
     launchCounter = 0;
-    seedQueue.clear();
-    seedQueueHead = 0;
+    windowRows = windowFill = 0;
     if (!mesh || !mesh->loadedMesh) {
         ok = false;
         lastError = "Init: mesh not loaded";
@@ -83,62 +83,90 @@ void RayTracer::UpdatePhotonsPerLight()
 void RayTracer::ComputeDosageMap()
 {
     if (!ok || lightPositions.empty()) return;
-    // SEED of every launch of the remaining passes in one device call, unless the queue built by
-    // an earlier pass still matches the route
-    const size_t L = lightPositions.size();
-    std::vector<float> pos(3 * L);
-    for (size_t i = 0; i < L; i++) {
-        pos[3 * i + 0] = lightPositions[i].position.x;
-        pos[3 * i + 1] = mesh->floorHeight + lightHeight;
-        pos[3 * i + 2] = lightPositions[i].position.y;
-    }
-    bool queued = seedQueue.size() - seedQueueHead >= L &&
-                  memcmp(&seedQueuePos[3 * seedQueueHead], pos.data(), sizeof(float) * 3 * L) == 0;
-    if (!queued) {
-        int passes = maxIterations - currIterations;
-        if (passes < 1) passes = 1;
-        std::vector<float> all(3 * L * (size_t)passes);
-        for (int p = 0; p < passes; p++) memcpy(&all[3 * L * p], pos.data(), sizeof(float) * 3 * L);
-        std::vector<uint32_t> seeds(L * (size_t)passes + 1);
-        if (!Check(uvrt_seed_chain(ctx, all.data(), (int)(L * passes), lightLength, seedState, seeds.data()), "seed_chain")) return;
-        seedQueue.assign(seeds.begin() + 1, seeds.end());
-        seedQueuePos.swap(all);
-        seedQueueHead = 0;
-    }
     for (LightPos& lightPosition : lightPositions) {
         ComputeSingleLightDosageMap(lightPosition, photonsPerLight, mesh->triangleCount);
     }
 }
 
-// Which rank traces launch k of a run over a route of L positions.  Plain round-robin (k mod N) would
-// hand a rank the same few positions in every pass whenever gcd(L, N) > 1 (L = 12, N = 8: three
-// positions per rank), and positions differ in cost by up to 1.5x (24.9 - 36.6 node visits per ray on
-// lange_route), so the slowest rank would set the pace.  The deal is therefore rotated by s ranks per
-// pass, with the smallest s that makes L + s coprime to N: every position then visits every rank.
-int RayTracer::ShardOwner(long long launch, int L, int N)
+// Which rank traces unit u of a run with U units per pass.  Plain round-robin (u mod N) would hand a rank the
+// same few positions in every pass whenever gcd(U, N) > 1 (12 positions, 8 ranks: three positions per rank),
+// and positions differ in cost by up to 1.5x (24.9 - 36.6 node visits per ray on lange_route), so the slowest
+// rank would set the pace.  The deal is therefore rotated by s ranks per pass, with the smallest s that makes
+// U + s coprime to N: every position then visits every rank.
+int RayTracer::ShardOwner(long long unit, int U, int N)
 {
     if (N <= 1) return 0;
-    if (L < 1) L = 1;
+    if (U < 1) U = 1;
     auto gcd = [](long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; };
     int s = 0;
-    while (gcd((long long)L + s, N) != 1) s++;
-    const long long pass = launch / L;
-    return (int)((launch + (long long)s * pass) % N);
+    while (gcd((long long)U + s, N) != 1) s++;
+    const long long pass = unit / U;
+    return (int)((unit + (long long)s * pass) % N);
 }
 
-uint32_t RayTracer::SeedAfter(const float3& lp)
+// Ray ranges per launch of a sharded run: whole launches keep the rays of a launch together (the ray binning
+// of extend works best on a full launch), but a run of few launches then leaves the ranks unevenly loaded
+// (120 launches on 8 GPUs: 15 each, and positions differ in cost: 8.6 % imbalance in the cost model of
+// DESIGN.md section 4); halves or quarters even that out.
+int RayTracer::AutoParts() const
 {
-    if (seedQueueHead < seedQueue.size()) {
-        const float* q = &seedQueuePos[3 * seedQueueHead];
-        if (!memcmp(&q[0], &lp.x, 4) && !memcmp(&q[1], &lp.y, 4) && !memcmp(&q[2], &lp.z, 4))
-            return seedQueue[seedQueueHead++];
-        seedQueue.clear();   // the route changed under us: fall back to one launch at a time
-        seedQueueHead = 0;
-    }
-    float pos[3] = {lp.x, lp.y, lp.z};
-    uint32_t seeds[2] = {seedState, seedState};
-    Check(uvrt_seed_chain(ctx, pos, 1, lightLength, seedState, seeds), "seed_chain");
-    return seeds[1];
+    if (shardParts > 0) return shardParts;
+    if (shardCount <= 1 || lightPositions.empty()) return 1;
+    long long launches = (long long)lightPositions.size() * (maxIterations > 0 ? maxIterations : 1);
+    int parts = 1;
+    while (parts < 8 && launches * parts < 48LL * shardCount && photonsPerLight / (2 * parts) >= (1 << 19)) parts *= 2;
+    return parts;
+}
+
+// generate.cl:13-39 for work-item 0 (the only one that writes SEED): the seed expression in fp32 from left to
+// right, float -> uint saturating, two draws for the origin offset and diry, then pairs of
+// draws until the point lies inside the unit disc.  This library is built with -ffp-contract=off.
+uint32_t RayTracer::SeedAfterLaunch(float lx, float ly, float lz, float /*lightLength*/, uint32_t seedIn)
+{
+    auto xorshift = [](uint32_t& s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; };
+    auto uniform = [&](uint32_t& s) { return (float)xorshift(s) * 2.3283064365387e-10f; };
+    float e = (float)(0 * 17 + 1);
+    e = e + lx * 13.0f;
+    e = e + ly * 7.0f;
+    e = e + lz * 11.0f;
+    e = e + (float)(seedIn >> 15);
+    uint32_t s = !(e > 0.0f) ? 0u : (e >= 4294967296.0f ? 0xffffffffu : (uint32_t)e);
+    s = (s ^ 61u) ^ (s >> 16);
+    s *= 9u;
+    s = s ^ (s >> 4);
+    s *= 0x27d4eb2du;
+    s = s ^ (s >> 15);
+    uniform(s);                       // origin offset along the lamp (generate.cl:16)
+    uniform(s);                       // diry (generate.cl:22)
+    double x, z;
+    do {                              // generate.cl:25-28; a work-item stuck at RNG state 0 keeps its first draw
+        float fx = uniform(s) * 2.0f - 1.0f;
+        float fz = uniform(s) * 2.0f - 1.0f;
+        x = (double)fx;
+        z = (double)fz;
+    } while (x * x + z * z > 1.0 && s != 0u);
+    return s;
+}
+
+void RayTracer::BeginWindow()
+{
+    const long long L = (long long)lightPositions.size();
+    long long remaining = L;
+    if (launchCounter % L == 0 && maxIterations > currIterations) remaining = (long long)(maxIterations - currIterations) * L;
+    // one int32 row per launch: at most 256 MiB of rows at a time
+    long long maxRows = (256LL << 20) / (4LL * (mesh->triangleCount > 0 ? mesh->triangleCount : 1));
+    if (maxRows < 1) maxRows = 1;
+    if (maxRows > 4096) maxRows = 4096;
+    windowRows = (int)(remaining < maxRows ? remaining : maxRows);
+    windowFill = 0;
+    windowDurations.assign((size_t)windowRows, 0.0f);
+    Check(uvrt_matrix_begin(ctx, windowRows), "matrix_begin");
+}
+
+void RayTracer::FoldWindow()
+{
+    if (windowFill > 0) Check(uvrt_matrix_fold(ctx, windowDurations.data(), windowFill, 1), "matrix_fold");
+    windowRows = windowFill = 0;
 }
 
 // photonsPerLight and triangleCount are parameters because CalibratePower() uses its own values.
@@ -147,15 +175,31 @@ void RayTracer::ComputeSingleLightDosageMap(LightPos lightPos, int photonsPerLig
 {
     if (!ok) return;
     float3 lightposition = make_float3(lightPos.position.x, mesh->floorHeight + lightHeight, lightPos.position.y);
-    const bool mine = shardCount <= 1 || ShardOwner(launchCounter, (int)lightPositions.size(), shardCount) == shardRank;
-    if (mine) {
+    if (shardCount <= 1) {
         if (!Check(uvrt_trace(ctx, lightposition.x, lightposition.y, lightposition.z, lightLength, lightPos.duration, 0,
                               photonsPerLight, seedState),
                    "trace"))
             return;
         raysTraced += photonsPerLight;
+    } else {
+        if (windowRows == 0) BeginWindow();
+        if (!ok) return;
+        const int parts = AutoParts();
+        const int U = (int)lightPositions.size() * parts;
+        for (int j = 0; j < parts; j++) {
+            if (ShardOwner(launchCounter * parts + j, U, shardCount) != shardRank) continue;
+            const long long first = (long long)photonsPerLight * j / parts, last = (long long)photonsPerLight * (j + 1) / parts;
+            if (last <= first) continue;
+            if (!Check(uvrt_trace_row(ctx, windowFill, lightposition.x, lightposition.y, lightposition.z, lightLength, first,
+                                      last - first, seedState),
+                       "trace_row"))
+                return;
+            raysTraced += last - first;
+        }
+        windowDurations[(size_t)windowFill] = lightPos.duration;
+        if (++windowFill == windowRows) FoldWindow();
     }
-    seedState = SeedAfter(lightposition);
+    seedState = SeedAfterLaunch(lightposition.x, lightposition.y, lightposition.z, lightLength, seedState);
     launchCounter++;
     // the reference's `int photonMapSize` (raytracer.h:56) overflows after 2^31 photons (64 default
     // iterations): count in 64 bits and let the int field saturate instead of wrapping
@@ -183,7 +227,7 @@ void RayTracer::Shade()
 void RayTracer::Reduce()
 {
     if (!ok) return;
-    Check(uvrt_reduce(ctx), "reduce");
+    FoldWindow();
 }
 
 const float* RayTracer::ReadDosageMap()
@@ -209,6 +253,7 @@ void RayTracer::ResetDosageMap()
     currIterations = 0;
     launchCounter = 0;
     raysTraced = 0;
+    windowRows = windowFill = 0;
     ClearBuffers(true);
 }
 
@@ -339,31 +384,47 @@ bool RayTracer::SaveDosageMap(const char* basePath)
 
 namespace {
 struct CheckpointHeader {
-    char magic[8];            // "UVRTCKP1"
+    char magic[8];            // "UVRTCKP2"
     int32_t triangles, positions, currIterations, photonsPerLight;
     int64_t launchCounter, photonMapSizeTotal, raysTraced;
-    uint32_t seedState, pad;
+    uint32_t seedState;
+    int32_t shardCount;       // ranks of the run that wrote it (informational: the maps below are complete)
+    float lightLength, lightHeight;
 };
 } // namespace
 
+// The maps of a checkpoint are always COMPLETE: a sharded run folds its pending count-matrix rows first
+// (Reduce(): a collective, so every rank must call SaveCheckpoint at the same launch; the ranks then hold
+// identical maps and any one of them may write the file).  Loading it under any shard setup is therefore safe:
+// later windows add the all-reduced counts to every rank's copy alike.
 bool RayTracer::SaveCheckpoint(const char* path)
 {
     if (!ok || !mesh) return false;
+    Reduce();
+    if (!ok) return false;
     const size_t n = (size_t)mesh->triangleCount;
     std::vector<double> maps(2 * n);
     if (!Check(uvrt_read(ctx, UVRT_BUF_SUM, maps.data(), n * 8), "read photon map")) return false;
     if (!Check(uvrt_read(ctx, UVRT_BUF_MAX, maps.data() + n, n * 8), "read max map")) return false;
     CheckpointHeader h;
     memset(&h, 0, sizeof h);
-    memcpy(h.magic, "UVRTCKP1", 8);
+    memcpy(h.magic, "UVRTCKP2", 8);
     h.triangles = (int32_t)n; h.positions = (int32_t)lightPositions.size(); h.currIterations = currIterations;
     h.photonsPerLight = photonsPerLight; h.launchCounter = launchCounter; h.photonMapSizeTotal = photonMapSizeTotal;
-    h.raysTraced = raysTraced; h.seedState = seedState;
-    std::ofstream f(path, std::ios::binary);
-    if (!f) { lastError = std::string("SaveCheckpoint: cannot write ") + path; return false; }
-    f.write((const char*)&h, sizeof h);
-    f.write((const char*)maps.data(), (std::streamsize)(maps.size() * 8));
-    return (bool)f;
+    h.raysTraced = raysTraced; h.seedState = seedState; h.shardCount = shardCount;
+    h.lightLength = lightLength; h.lightHeight = lightHeight;
+    // write next to the target and rename: a crash mid-write must not destroy the previous checkpoint
+    const std::string tmp = std::string(path) + ".tmp";
+    {
+        std::ofstream f(tmp, std::ios::binary);
+        if (!f) { lastError = std::string("SaveCheckpoint: cannot write ") + tmp; return false; }
+        f.write((const char*)&h, sizeof h);
+        f.write((const char*)maps.data(), (std::streamsize)(maps.size() * 8));
+        f.flush();
+        if (!f) { lastError = std::string("SaveCheckpoint: write failed: ") + tmp; std::remove(tmp.c_str()); return false; }
+    }
+    if (std::rename(tmp.c_str(), path) != 0) { lastError = std::string("SaveCheckpoint: cannot rename to ") + path; std::remove(tmp.c_str()); return false; }
+    return true;
 }
 
 bool RayTracer::LoadCheckpoint(const char* path)
@@ -372,12 +433,18 @@ bool RayTracer::LoadCheckpoint(const char* path)
     const size_t n = (size_t)mesh->triangleCount;
     std::ifstream f(path, std::ios::binary);
     CheckpointHeader h;
-    if (!f || !f.read((char*)&h, sizeof h) || memcmp(h.magic, "UVRTCKP1", 8) != 0) {
+    if (!f || !f.read((char*)&h, sizeof h) || memcmp(h.magic, "UVRTCKP2", 8) != 0) {
         lastError = std::string("LoadCheckpoint: not a checkpoint: ") + path;
         return false;
     }
     if ((size_t)h.triangles != n || (size_t)h.positions != lightPositions.size()) {
         lastError = "LoadCheckpoint: checkpoint belongs to another room or route";
+        return false;
+    }
+    // the rays of the remaining launches depend on these: a mismatch would silently mix two different runs
+    if (h.photonsPerLight != photonsPerLight || memcmp(&h.lightLength, &lightLength, 4) != 0 || memcmp(&h.lightHeight, &lightHeight, 4) != 0) {
+        lastError = "LoadCheckpoint: checkpoint was written with other photon / lamp settings (photons per light " +
+                    std::to_string(h.photonsPerLight) + " vs " + std::to_string(photonsPerLight) + ")";
         return false;
     }
     std::vector<double> maps(2 * n);
@@ -391,8 +458,7 @@ bool RayTracer::LoadCheckpoint(const char* path)
     photonMapSize = photonMapSizeTotal > 0x7fffffffLL ? 0x7fffffff : (int)photonMapSizeTotal;
     raysTraced = h.raysTraced;
     seedState = h.seedState;
-    seedQueue.clear();
-    seedQueueHead = 0;
+    windowRows = windowFill = 0;
     startedComputation = true;
     finishedComputation = currIterations >= maxIterations;
     return true;

@@ -69,15 +69,24 @@ public:
     // Device-side SEED of generate.cl:6 as seen by the next launch: starts at 0
     // and, like the reference's program-scope variable, survives ResetDosageMap().
     uint32_t seedState = 0;
-    // Work sharing between GPUs: launch k (counted over the whole run) is traced by the rank
-    // ShardOwner(k, positions, shardCount) -- round-robin, rotated once per pass so that every rank sees
-    // every position; every rank advances seedState and photonMapSize for every launch.
-    static int ShardOwner(long long launch, int positions, int ranks);
+    // Work sharing between GPUs.  Every launch of a run is cut into shardParts ray ranges (1 = whole launches);
+    // unit u = launch * parts + part is traced by rank ShardOwner(u, positions * parts, shardCount) -- round-robin,
+    // rotated once per pass so that every rank sees every lamp position.  A range passes its first global ray
+    // id, so its rays are those of the unsplit launch.  Every rank advances seedState and photonMapSize for every
+    // launch.  Sharded runs collect integer counts in a count matrix (one row per launch, uvrt.h) that Reduce()
+    // sums over the ranks and folds in launch order: maps bit-identical to the single-GPU run for any split.
+    static int ShardOwner(long long unit, int unitsPerPass, int ranks);
     int shardRank = 0, shardCount = 1;
+    int shardParts = 0;          // 0: chosen per run (AutoParts)
+    int AutoParts() const;
     long long launchCounter = 0;
     long long photonMapSizeTotal = 0;   // photonMapSize without the int overflow (see ComputeSingleLightDosageMap)
-    // Cross-rank sum (photon map) and max (max map); needs uvrt_comm_init on ctx.  Call once,
-    // after the last ComputeDosageMap() and before Shade().
+    // SEED after a launch at lightposition (generate.cl:13-39 for work-item 0), computed on the host: the chain
+    // of a whole run needs no device round trip.  Bit-identical to the device (uvrt_seed_chain; GPU test).
+    static uint32_t SeedAfterLaunch(float lx, float ly, float lz, float lightLength, uint32_t seedIn);
+    // Sharded runs: sums the pending rows of the count matrix over the ranks (one ncclAllReduce; needs
+    // uvrt_comm_init on ctx) and folds them into the photon / max maps.  Call after the last ComputeDosageMap()
+    // and before Shade() / ReadDosageMap(); long runs also fold whenever the matrix window is full.
     void Reduce();
     // Copies the per-triangle dose (after Shade) into dosageMap, resized to triangleCount floats.
     const float* ReadDosageMap();
@@ -97,10 +106,11 @@ public:
 private:
     bool Check(int rc, const char* what);
     void UploadScene();
-    uint32_t SeedAfter(const float3& lightposition);
-    std::vector<uint32_t> seedQueue;        // precomputed SEED values for the next launches
-    std::vector<float> seedQueuePos;        // their lamp positions (xyz), to validate the queue
-    size_t seedQueueHead = 0;
+    // count-matrix window of a sharded run
+    void BeginWindow();
+    void FoldWindow();
+    int windowRows = 0, windowFill = 0;
+    std::vector<float> windowDurations;
     int dosageMapSize = 2;
     int64_t raysTraced = 0;
 };

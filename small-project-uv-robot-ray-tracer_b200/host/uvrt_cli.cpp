@@ -63,7 +63,10 @@ int main(int argc, char** argv)
 
     if (jsonLine) uvrt_set_option(rayTracer.ctx, "stage_timing", 1);
     rayTracer.ResetDosageMap();
-    if (!resume.empty() && !rayTracer.LoadCheckpoint(resume.c_str())) { fprintf(stderr, "%s\n", rayTracer.lastError.c_str()); return 1; }
+    if (!resume.empty()) {
+        if (!rayTracer.LoadCheckpoint(resume.c_str())) { fprintf(stderr, "%s\n", rayTracer.lastError.c_str()); return 1; }
+        rayTracer.Shade();     // a checkpoint of a finished run skips the loop below: the dose map must still be formed
+    }
     while (rayTracer.ok) {
         rayTracer.finishedComputation = rayTracer.currIterations >= rayTracer.maxIterations;
         if (rayTracer.finishedComputation) break;

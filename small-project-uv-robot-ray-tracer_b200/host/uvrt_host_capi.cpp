@@ -223,19 +223,20 @@ int uvrt_sim_shade(uvrt_sim* s)
     return rt_status(s);
 }
 
-int uvrt_sim_tick(uvrt_sim* s, int* finished)
+// One frame of MyApp::Tick.  sync: the reference ends every frame with clFinish (myapp.cpp:165); a whole run
+// (uvrt_sim_run) only synchronises once at its end, so the launches of consecutive passes keep overlapping.
+static int sim_tick(uvrt_sim* s, int* finished, bool sync)
 {
-    if (!s || !s->rt.ctx) return UVRT_ERR_INVALID;
     RayTracer& rt = s->rt;
     if (!rt.finishedComputation) {
         rt.finishedComputation = rt.currIterations >= rt.maxIterations;
         if (!rt.finishedComputation) {
             rt.ComputeDosageMap();
-            if (rt.shardCount <= 1) rt.Shade();   // a partial map is not worth shading
+            if (rt.shardCount <= 1 && sync) rt.Shade();   // a partial map is not worth shading; a run shades once at its end
             if (rt.viewMode == texture) rt.viewMode = dosage;
             rt.currIterations++;
             rt.progress = 100.0f * (float)rt.currIterations / (float)rt.maxIterations;
-            if (rt.ok && uvrt_sync(rt.ctx) != UVRT_OK) { rt.ok = false; rt.lastError = uvrt_last_error(rt.ctx); }
+            if (sync && rt.ok && uvrt_sync(rt.ctx) != UVRT_OK) { rt.ok = false; rt.lastError = uvrt_last_error(rt.ctx); }
             rt.compTime += rt.timerClock.elapsed();
             rt.timerClock.reset();
         }
@@ -244,18 +245,22 @@ int uvrt_sim_tick(uvrt_sim* s, int* finished)
     return rt_status(s);
 }
 
+int uvrt_sim_tick(uvrt_sim* s, int* finished)
+{
+    if (!s || !s->rt.ctx) return UVRT_ERR_INVALID;
+    return sim_tick(s, finished, true);
+}
+
 int uvrt_sim_run(uvrt_sim* s, float* dose, int capacity)
 {
     if (!s || !s->rt.ctx) return UVRT_ERR_INVALID;
     RayTracer& rt = s->rt;
     rt.ResetDosageMap();
     int finished = 0, rc = UVRT_OK;
-    while (!finished && rc == UVRT_OK) rc = uvrt_sim_tick(s, &finished);
+    while (!finished && rc == UVRT_OK) rc = sim_tick(s, &finished, false);
     if (rc != UVRT_OK) return rc;
-    if (rt.shardCount > 1) {
-        rt.Reduce();
-        rt.Shade();
-    }
+    rt.Reduce();               // sharded runs: all-reduce + fold of the pending count-matrix rows; otherwise a no-op
+    rt.Shade();
     if (dose) return uvrt_sim_read_dose(s, dose, capacity);
     if (rt.ok && uvrt_sync(rt.ctx) != UVRT_OK) { rt.ok = false; rt.lastError = uvrt_last_error(rt.ctx); }
     return rt_status(s);
@@ -285,6 +290,27 @@ int uvrt_sim_set_shard(uvrt_sim* s, int rank, int count)
     s->rt.shardRank = rank;
     s->rt.shardCount = count;
     return UVRT_OK;
+}
+
+int uvrt_sim_set_shard_parts(uvrt_sim* s, int parts)
+{
+    if (!s || parts < 0 || parts > 64) return UVRT_ERR_INVALID;
+    s->rt.shardParts = parts;
+    return UVRT_OK;
+}
+
+int uvrt_sim_shard_parts(const uvrt_sim* s) { return s ? s->rt.AutoParts() : 0; }
+
+int uvrt_sim_set_seed(uvrt_sim* s, uint32_t seed)
+{
+    if (!s) return UVRT_ERR_INVALID;
+    s->rt.seedState = seed;
+    return UVRT_OK;
+}
+
+uint32_t uvrt_host_seed_after_launch(float lx, float ly, float lz, float lightLength, uint32_t seedIn)
+{
+    return RayTracer::SeedAfterLaunch(lx, ly, lz, lightLength, seedIn);
 }
 
 int uvrt_sim_reduce(uvrt_sim* s)

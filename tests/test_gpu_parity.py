@@ -88,6 +88,8 @@ def test_seed_chain_matches_golden(uv, ctx, room, golden):
 def test_extend_bit_exact(uv, ctx, room, golden, variant, hist, binned):
     if hist and variant < 10:
         pytest.skip("hist_mode only exists for the persistent kernels")
+    if variant >= 10 and not ctx.get_option("experiments"):
+        pytest.skip("rejected variants are only compiled with `make EXPERIMENTS=1`")
     lp = lange_pos0(room[3])
     P = 1000000
     gen, want, want_counts, _, _ = oracle_launch(room, lp, P)
@@ -135,6 +137,8 @@ def test_full_size_launch_matches_golden(uv, ctx, room, golden):
 def test_extend_degenerate_rays(uv, ctx, room, variant, binned):
     """Axis-parallel directions (division by zero, 0/0 = NaN on slab planes), origins outside the
     room, zero-length directions: the strict path must reproduce the oracle's IEEE behaviour."""
+    if variant >= 10 and not ctx.get_option("experiments"):
+        pytest.skip("rejected variants are only compiled with `make EXPERIMENTS=1`")
     tris, nodes, tri_idx, floor = room
     rng = np.random.default_rng(5)
     n = 70000 if binned else 20000      # binning starts at 65,536 rays
@@ -286,12 +290,15 @@ def test_sharded_run_equals_single(uv, room):
         sim.init("route")
         sim.set_params(photonCount=1 << 21, maxIterations=3)
         sim.set_shard(rank, count)
+        sim.set_shard_parts(1)                   # whole launches: per-rank maxima can be combined with max()
         sim.reset_dosage_map()
         while not sim.tick():
             pass
+        sim.reduce()                             # no communicator: folds this "rank's" rows of the count matrix
         c = sim.ctx
         results.append((c.read(uv.BUF.SUM), c.read(uv.BUF.MAX), sim.params.seedState, sim.params.photonMapSize, sim.rays_traced()))
         sim.close()
+        sim = None
     one, a, b = results
     assert np.array_equal(one[0], a[0] + b[0])
     assert np.array_equal(one[1], np.maximum(a[1], b[1]))
@@ -843,3 +850,61 @@ def test_cuda_path_against_the_compiled_reference_directly(uv, ctx, room):
     assert ctx.read(uv.BUF.DOSE).tobytes() == dose.tobytes() and ctx.read(uv.BUF.COLOR).tobytes() == col.tobytes()
     assert int(ctx.seed_chain([lp], 1.0, 99)[1]) == so.value
     ctx.reset(True)
+
+
+def test_count_matrix_ray_ranges_fold_to_single_context_result(uv, ctx, room):
+    """launches cut into ray ranges over two 'ranks' (two contexts on one GPU), integer count
+    rows exchanged and summed by the caller (UVRT_BUF_MATRIX; on real ranks uvrt_matrix_fold does it with one
+    ncclAllReduce), folded in launch order: photon map AND per-launch max map bit-identical to one context running
+    uvrt_trace launch by launch -- with durations whose products do not add exactly."""
+    f32 = np.float32
+    tris, nodes, tri_idx, floor = room
+    lamps = [(f32(-0.255), f32(floor + f32(0.6)), f32(-3.31)), (f32(0.085), f32(floor + f32(0.6)), f32(-2.46)),
+             (f32(-0.51), f32(floor + f32(0.6)), f32(-1.19)), (f32(0.3), f32(floor + f32(0.6)), f32(2.0))]
+    durs = np.array([0.1, 7.3, 60.0, 1e-3], dtype=np.float32)
+    P = 300_001
+    seeds = [0]
+    for lp in lamps:
+        seeds.append(int(ctx.seed_chain([lp], 1.0, seeds[-1])[1]))
+    ctx.reset(True)
+    for lp, dur, seed in zip(lamps, durs, seeds):
+        ctx.trace(lp, 1.0, dur, 0, P, seed)
+    want_sum, want_max = ctx.read(uv.BUF.SUM), ctx.read(uv.BUF.MAX)
+    cuts = [0, 70_001, 70_001, 200_000, P]                     # ranges of unequal size, one of them empty
+    ranks = [uv.Context(0), uv.Context(0)]
+    mats = []
+    for r, c in enumerate(ranks):
+        c.upload_scene(tris, nodes, tri_idx)
+        c.reset(True)
+        c.matrix_begin(len(lamps))
+        for row, (lp, seed) in enumerate(zip(lamps, seeds)):
+            for j in range(len(cuts) - 1):
+                if (row + j) % 2 == r and cuts[j + 1] > cuts[j]:
+                    c.trace_row(row, lp, 1.0, cuts[j], cuts[j + 1] - cuts[j], seed)
+        mats.append(c.read(uv.BUF.MATRIX, len(lamps)))
+    total = mats[0] + mats[1]
+    for c in ranks:
+        c.write(uv.BUF.MATRIX, total)
+        c.matrix_fold(durs, reduce=False)
+        assert c.read(uv.BUF.SUM).tobytes() == want_sum.tobytes()
+        assert c.read(uv.BUF.MAX).tobytes() == want_max.tobytes()
+        c.close()
+    assert mats[0].any() and mats[1].any()
+    ctx.reset(True)
+
+
+def test_host_seed_chain_equals_device_seed_chain(uv, ctx, room):
+    """RayTracer advances SEED on the host (RayTracer::SeedAfterLaunch); uvrt_seed_chain replays work-item 0 on the device."""
+    H = uv.host()
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_route("lange_route")
+    pos, p = sim.positions, sim.params
+    sim.close()
+    f32 = np.float32
+    lps = [(f32(x), f32(f32(room[3]) + f32(p.lightHeight)), f32(y)) for x, y, _ in pos] * 3 + [(f32(0.0), f32(0.5), f32(-2.5454545))]
+    for seed0 in (0, 2, 0xfffffff0):
+        chain = ctx.seed_chain(lps, p.lightLength, seed0)
+        seed = seed0
+        for k, lp in enumerate(lps):
+            seed = int(H.uvrt_host_seed_after_launch(lp[0], lp[1], lp[2], f32(p.lightLength), seed))
+            assert seed == int(chain[k + 1])

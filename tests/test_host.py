@@ -402,3 +402,66 @@ def test_loaders_survive_corrupt_files(uv, tmp_path):
         sim.load_route("f")                      # never raises: a broken file leaves the settings alone
         assert sim.params.photonCount is not None
     uv.Sim(asset_root=T.DATA)  # restore the asset root for later tests
+
+
+# ---- T0 as SURVEY section 4 wrote it: this repo's readers against the reference's OWN loaders ------------------
+def _ref_loader():
+    path = os.path.join(T.ORACLE_DIR, "_ref", "libuvrt_ref_loader.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libuvrt_ref_loader.so not built (needs /root/reference with lib/tinygltf-master, lib/tinyxml2)")
+    lib = C.CDLL(path)
+    lib.refload_mesh.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_uint)]
+    lib.refload_free.argtypes = [C.c_void_p]
+    lib.refload_route.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p]
+    return lib
+
+
+class _RefRoute(C.Structure):
+    _fields_ = [("photonCount", C.c_int), ("maxIterations", C.c_int), ("lightIntensity", C.c_float), ("minDosage", C.c_float),
+                ("minPower", C.c_float), ("lightLength", C.c_float), ("lightHeight", C.c_float), ("photonsPerLight", C.c_int),
+                ("positions", C.c_int)]
+
+
+def test_glb_loader_equals_the_references_own_loader(checkers, room):
+    """Mesh::LoadMesh + DetermineFloorHeight of the reference (mesh.cpp:5-136, compiled unmodified with its vendored
+    tinygltf) against host/mesh.cpp (own GLB reader): Tri[] vertex and centroid lanes bit-equal, same floor height."""
+    R = _ref_loader()
+    tris, nodes, tri_idx, floor = room
+    p, n, fh, used = C.c_void_p(), C.c_int(), C.c_float(), C.c_uint()
+    assert R.refload_mesh(T.DATA.encode(), b"testroomopt", C.byref(p), C.byref(n), C.byref(fh), C.byref(used)) == 0
+    try:
+        ref_tris = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n.value, 16)).copy()
+    finally:
+        R.refload_free(p)
+    assert n.value == tris.shape[0] == 44866
+    lanes = [0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14]            # the pad lanes are uninitialised in the reference (mesh.cpp:53)
+    assert ref_tris[:, lanes].tobytes() == tris[:, lanes].tobytes()
+    assert np.float32(fh.value).tobytes() == np.float32(floor).tobytes()
+    assert used.value == 2 * n.value                               # the reference reports 2N (bvh.cpp:43); this repo the true extent
+    assert len(nodes) > 2 * n.value
+
+
+@pytest.mark.parametrize("name", ["route", "lange_route"])
+def test_route_loader_equals_the_references_own_loader(checkers, uv, tmp_path, name):
+    """RayTracer::LoadRoute / SaveRoute of the reference (raytracer.cpp:228-300 with its vendored tinyxml2) against
+    host/raytracer.cpp + xml_min.h: every field and position bit-equal, and the files the two SaveRoutes write are
+    byte-identical."""
+    R = _ref_loader()
+    root = tmp_path / "assets"
+    (root / "positions").mkdir(parents=True)
+    shutil.copy(os.path.join(T.DATA, "positions", name + ".xml"), root / "positions" / (name + ".xml"))
+    out = _RefRoute()
+    xyd = np.zeros((64, 3), dtype=np.float32)
+    assert R.refload_route(str(root).encode(), name.encode(), C.byref(out), T.ptr(xyd), 64, b"ref_saved") == 0
+    sim = uv.Sim(asset_root=str(root))
+    sim.load_route(name)
+    p, pos = sim.params, sim.positions
+    sim.save_route("own_saved")
+    sim.close()
+    f32 = np.float32
+    assert (out.photonCount, out.maxIterations, out.positions, out.photonsPerLight) == (p.photonCount, p.maxIterations, len(pos), p.photonsPerLight)
+    for a, b in ((out.lightIntensity, p.lightIntensity), (out.minDosage, p.minDosage), (out.minPower, p.minPower),
+                 (out.lightLength, p.lightLength), (out.lightHeight, p.lightHeight)):
+        assert f32(a).tobytes() == f32(b).tobytes()
+    assert xyd[: len(pos)].tobytes() == pos.tobytes()
+    assert (root / "positions" / "ref_saved.xml").read_bytes() == (root / "positions" / "own_saved.xml").read_bytes()

@@ -1,8 +1,11 @@
-"""The N > 1 contract on the CPU (gloo, world_size 2): launches are dealt round-robin, rotated once
-per pass (RayTracer::ShardOwner, called here through libuvrt_host), every rank advances the SEED
-chain for all launches, and ONE reduction -- sum of the photon maps, max of the per-launch maxima --
-reproduces the single-rank result exactly.  The per-launch work is done by the oracle here; the same
-check runs on real GPUs over NCCL in tools/multi_gpu_check.py."""
+"""The N > 1 contract on the CPU (gloo, world_size 2): every launch is cut into ray ranges, unit
+launch * parts + part goes to rank RayTracer::ShardOwner(unit, positions * parts, N) (called here through
+libuvrt_host), a range passes its first global ray id so its rays are those of the unsplit launch, every rank
+advances the SEED chain on the host for all launches (RayTracer::SeedAfterLaunch), the ranks' INTEGER counts meet
+in a count matrix (one row per launch) that ONE all-reduce sums, and folding the rows in launch order
+(accumulate.cl:4-14) reproduces the single-rank photon map and max map bit for bit -- for any split and for
+durations whose products do not add exactly in f64.  The per-range work is done by the oracle here; the same
+protocol runs on real GPUs over NCCL in tools/multi_gpu_check.py / tests/test_gpu_multi.py."""
 import os
 import subprocess
 import sys
@@ -26,29 +29,41 @@ d = np.load(os.environ["UVRT_SCENE"])
 tris, nodes, tri_idx = d["tris"], d["nodes"].view(T.NODE_DT).reshape(-1), d["tri_idx"]
 pos, floor = d["pos"], np.float32(d["floor"])
 O = T.oracle()
-n = tris.shape[0]; P = 40000; f32 = np.float32
-def run(world, rank):
-    pm, mx, temp = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32)
+n = tris.shape[0]; P = 40001; f32 = np.float32
+def run(world, rank, parts):
+    L = len(pos)
+    matrix = np.zeros((2 * L, n), dtype=np.int32)
+    durs = []
     rays = np.zeros(P, dtype=T.RAY_DT); seed = 0; k = 0
     for it in range(2):
         for (x, y, dur) in pos:
-            so = C.c_uint32(0)
             lp = (f32(x), f32(floor + f32(0.6)), f32(y))
-            if H.uvrt_host_shard_owner(k, len(pos), world) == rank:
-                O.orc_generate(T.ptr(rays), 0, P, lp[0], lp[1], lp[2], f32(1.0), seed, C.byref(so))
-                O.orc_extend(T.ptr(temp), T.ptr(tris), T.ptr(rays), T.ptr(nodes), T.ptr(tri_idx), P, 1, None)
-                O.orc_accumulate(T.ptr(pm), T.ptr(mx), T.ptr(temp), f32(dur), n)
-            else:
-                O.orc_generate(T.ptr(rays), 0, 0, lp[0], lp[1], lp[2], f32(1.0), seed, C.byref(so))   # SEED only
-            seed = int(so.value); k += 1
-    return pm, mx, seed
-pm, mx, seed = run(world, rank)
-tp, tm = torch.from_numpy(pm), torch.from_numpy(mx)
-dist.all_reduce(tp, op=dist.ReduceOp.SUM)
-dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            for j in range(parts):
+                if H.uvrt_host_shard_owner(k * parts + j, L * parts, world) != rank:
+                    continue
+                first, last = P * j // parts, P * (j + 1) // parts
+                O.orc_generate(T.ptr(rays), first, last - first, lp[0], lp[1], lp[2], f32(1.0), seed, None)
+                O.orc_extend(T.ptr(matrix[k]), T.ptr(tris), T.ptr(rays), T.ptr(nodes), T.ptr(tri_idx), last - first, 1, None)
+            durs.append(f32(dur))
+            seed = int(H.uvrt_host_seed_after_launch(lp[0], lp[1], lp[2], f32(1.0), seed)); k += 1
+    return matrix, durs, seed
+def fold(matrix, durs):
+    pm, mx = np.zeros(n), np.zeros(n)
+    for row, dur in zip(matrix, durs):
+        temp = row.copy()
+        O.orc_accumulate(T.ptr(pm), T.ptr(mx), T.ptr(temp), dur, n)
+    return pm, mx
+ok = True
+for parts in (1, 3):
+    matrix, durs, seed = run(world, rank, parts)
+    t = torch.from_numpy(matrix)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    pm, mx = fold(t.numpy(), durs)
+    if rank == 0:
+        m1, d1, seed1 = run(1, 0, 1)
+        pm1, mx1 = fold(m1, d1)
+        ok = ok and pm1.tobytes() == pm.tobytes() and mx1.tobytes() == mx.tobytes() and seed == seed1 and np.array_equal(m1, t.numpy())
 if rank == 0:
-    pm1, mx1, seed1 = run(1, 0)
-    ok = pm1.tobytes() == tp.numpy().tobytes() and mx1.tobytes() == tm.numpy().tobytes() and seed == seed1
     print("MULTIRANK_OK" if ok else "MULTIRANK_MISMATCH", flush=True)
 dist.destroy_process_group()
 '''
@@ -56,7 +71,7 @@ dist.destroy_process_group()
 
 def test_round_robin_shards_reduce_to_single_rank_result(room, tmp_path, checkers):
     tris, nodes, tri_idx, floor = room
-    pos = np.array([[-0.255, -3.31, 60.0], [0.085, -2.46, 30.0], [-0.51, -1.19, 0.1]], dtype=np.float32)
+    pos = np.array([[-0.255, -3.31, 60.0], [0.085, -2.46, 30.7], [-0.51, -1.19, 0.1]], dtype=np.float32)
     scene = str(tmp_path / "scene.npz")
     np.savez(scene, tris=tris, nodes=nodes.view(np.uint8), tri_idx=tri_idx, pos=pos, floor=np.float32(floor))
     worker = tmp_path / "worker.py"
@@ -85,3 +100,25 @@ def test_shard_owner_rotates_positions_over_ranks():
             share[r] += 1
         assert all(len(v) == N for v in seen.values()), (L, N, seen)
         assert max(share) - min(share) <= 1 + L * passes // (N * 50), (L, N, share)
+
+
+def test_host_seed_chain_equals_oracle(checkers, room):
+    """RayTracer::SeedAfterLaunch (work-item 0 of generate.cl replayed on the host, no device round trip) against
+    the oracle's SEED_out: route positions, negative seed expressions (saturation), large seeds, and the work-item
+    whose RNG state is 0."""
+    import ctypes as C
+    import importlib
+    H = importlib.import_module("small-project-uv-robot-ray-tracer_b200").host()
+    O = checkers.oracle()
+    f32 = np.float32
+    rng = np.random.default_rng(11)
+    cases = [(f32(0.0), f32(0.0), f32(60.0 / 11.0), 0), (f32(0.0), f32(0.5), f32(-2.5454545), 2)]
+    for _ in range(300):
+        cases.append((f32(rng.uniform(-3, 3)), f32(rng.uniform(-2, 2)), f32(rng.uniform(-5, 6)), int(rng.integers(0, 2**32))))
+    seed = 0
+    for (x, y, z, s0) in cases:
+        for seed_in in (s0, seed):
+            so = C.c_uint32(0)
+            O.orc_generate(None, 0, 0, x, y, z, f32(1.0), seed_in, C.byref(so))
+            assert int(H.uvrt_host_seed_after_launch(x, y, z, f32(1.0), seed_in)) == so.value
+            seed = int(so.value)

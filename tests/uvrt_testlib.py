@@ -63,6 +63,7 @@ def oracle():
         lib.orc_fnv_hits.restype = C.c_uint64
         lib.orc_fnv_hits.argtypes = [C.c_void_p, C.c_int64]
         lib.orc_num_threads.restype = C.c_int
+        lib.orc_set_num_threads.argtypes = [C.c_int]
         _oracle = lib
     return _oracle
 
@@ -83,6 +84,8 @@ def ref():
         lib.ref_compute_dosage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
         lib.ref_dosage_to_color.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int]
         lib.ref_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.ref_num_threads.restype = C.c_int
+        lib.ref_set_num_threads.argtypes = [C.c_int]
         lib.ref_bvh_build.restype = C.c_int
         lib.ref_bvh_build.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _ref = lib
