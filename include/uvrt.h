@@ -166,7 +166,11 @@ int uvrt_matrix_fold(uvrt_ctx* ctx, const float* durations, int rows, int reduce
 /* Options (defaults are the measured best; everything else exists for A/B runs, see DESIGN.md section 4 and
  * profiles/r1_sweeps.md):
  *   "extend_variant"  kernel selection: 0/1/2 one thread per ray with IEEE / two-step / one-step (default) slab
- *                     division.  Builds with -DUVRT_EXPERIMENTS (`make EXPERIMENTS=1`, read-only option
+ *                     division; 50 / 51 the certified fast extend (csrc/uvrt_fast.cuh: conservative inner-node
+ *                     tests on 32-byte quantised / 64-byte fp32 node pairs, exact verification of every accepted
+ *                     hit, rays without a certificate re-traced in reference order; "fast_check" = 1 traces every
+ *                     ray both ways and counts disagreements, "fast_cfg" selects the register budget; read only:
+ *                     "scene_nested", "fast_ready").  Builds with -DUVRT_EXPERIMENTS (`make EXPERIMENTS=1`, read-only option
  *                     "experiments") also carry the rejected variants of profiles/r1_sweeps.md: 10..24 persistent
  *                     warps with a global queue, 40..43 chunk-persistent warps
  *   "bin_rays"        1 (default): counting sort of the ray queue by direction / origin cell before extend;
@@ -202,6 +206,13 @@ int uvrt_flush_l2(uvrt_ctx* ctx);
 int64_t uvrt_scene_upload_bytes(const uvrt_ctx* ctx);
 /* Traversal statistics of the repacked scene: inner nodes, leaves, depth, stack bound. */
 int uvrt_scene_info(uvrt_ctx* ctx, int* innerNodes, int* leaves, int* depth, int* stackEntries);
+
+/* Certified fast extend ("extend_variant" 50 / 51, csrc/uvrt_fast.cuh): counters since the last reset.
+ * out3 = {rays traced again in reference order because their certificate failed, rays not eligible for the fast
+ * path (not tame, origin far outside the scene, a hit already recorded), certified rays whose answer differed
+ * from the reference-order traversal -- counted only with option "fast_check" = 1, which traces every ray both
+ * ways; must be 0}.  Synchronises. */
+int uvrt_fast_stats(uvrt_ctx* ctx, unsigned long long* out3, int reset);
 
 /* Diagnostic: compares the shared-reciprocal slab division used by the fast extend variants with
  * IEEE division on blocks*256*itersPerThread random operand pairs.

@@ -116,6 +116,7 @@ def lib():
         "uvrt_elapsed_ms": (i, [vp, i, i, C.POINTER(f)]),
         "uvrt_scene_info": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
         "uvrt_selftest_division": (i, [vp, i, i, vp]),
+        "uvrt_fast_stats": (i, [vp, vp, i]),
         "uvrt_flush_l2": (i, [vp]),
         "uvrt_scene_upload_bytes": (i64, [vp]),
         "uvrt_version": (C.c_char_p, []),
@@ -346,6 +347,12 @@ class Context:
         out = np.zeros(3, dtype=np.uint64)
         self.check(self.L.uvrt_selftest_division(self.h, blocks, iters, _p(out)))
         return [int(x) for x in out]
+
+    def fast_stats(self, reset=False):
+        """{'cert_fallbacks', 'ineligible', 'check_mismatches'} of the certified fast extend since the last reset."""
+        out = np.zeros(3, dtype=np.uint64)
+        self.check(self.L.uvrt_fast_stats(self.h, _p(out), int(reset)))
+        return {"cert_fallbacks": int(out[0]), "ineligible": int(out[1]), "check_mismatches": int(out[2])}
 
     def comm_init(self, id128, rank, n_ranks):
         buf = (C.c_char * 128).from_buffer_copy(bytes(id128))

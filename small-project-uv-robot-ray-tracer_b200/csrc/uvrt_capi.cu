@@ -6,6 +6,7 @@
 #include "uvrt_kernels.cuh"
 #include "uvrt_bvh_build.cuh"
 #include "uvrt_scene_prep.cuh"
+#include "uvrt_fast.cuh"
 
 #include <dlfcn.h>
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler injects itself
@@ -113,6 +114,14 @@ struct uvrt_ctx {
     long long nSlots = 0;                // leaf triangle slots (= nTris for a tree that covers the mesh)
     uint32_t rootRef = 0;
     int sceneTame = 0;
+    int sceneNested = 0;                 // every child box inside its parent's box (checked by the repack)
+    // certified fast extend (uvrt_fast.cuh): 32-byte quantised node pairs, grid, fallback counters
+    uint4* dQPairs = nullptr;
+    size_t qpairCap = 0;                 // capacity in node pairs
+    FastGrid* dFastGrid = nullptr;
+    FastStats* dFastStats = nullptr;
+    int fastCheck = 0;                   // option "fast_check": trace every ray twice and count certified mismatches
+    int fastCfg = 0;                     // option "fast_cfg": register budget of the fast kernel
     cudaTextureObject_t pairsTex = 0;   // the same buffer as a 1-D float4 texture ("fetch_mode" experiment)
     int fetchMode = 3;   // 3: rays, permutation kept out of L1 (ld.global.L1::no_allocate); 0: plain loads; 1/2: texture experiments; 4: + evict_last nodes
     float4* dPairs = nullptr;   // nPairs x 4 float4
@@ -552,6 +561,22 @@ int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     else if (v == 2 && ctx->fetchMode == 5 && perm) launch_simple_fetch<5>(ctx, nRays, perm);
 #endif
     else if (v == 2) launch_simple<DIV_MARKSTEIN1>(ctx, nRays, perm);
+    else if (v == 50 || v == 51) {
+        // certified fast extend (50: 32-byte quantised node pairs, 51: conservative fp32 test on the exact kernel's pairs);
+        // scenes it cannot serve (boxes not tame / not nested, a single leaf) take the exact kernel
+        if (ctx->nPairs > 0 && ctx->sceneTame && ctx->sceneNested && ctx->dQPairs && nRays <= 0x7fffffffLL) {
+#define UVRT_FAST_LAUNCH(MINB, NODES)                                                                                      \
+    k_extend_fast<kStack, 128, MINB, NODES><<<grid_for(nRays, 128), 128, 0, ctx->xStream>>>(                                \
+        ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->dQPairs, ctx->dFastGrid, (uint32_t)nRays, perm, ctx->dFastStats, ctx->fastCheck)
+            // "fast_cfg": 0 = at most 48 registers (40 resident warps per SM, a few spills), 1 = at most 64 (32 warps, none)
+            if (v == 50 && ctx->fastCfg == 0) UVRT_FAST_LAUNCH(10, 0);
+            else if (v == 50) UVRT_FAST_LAUNCH(8, 0);
+            else if (ctx->fastCfg == 0) UVRT_FAST_LAUNCH(10, 1);
+            else UVRT_FAST_LAUNCH(8, 1);
+#undef UVRT_FAST_LAUNCH
+        } else
+            launch_simple_fetch<3>(ctx, nRays, perm);
+    }
 #ifdef UVRT_EXPERIMENTS
     else if (v >= 40 && v < 44) {
         // chunk-persistent warps (k_extend_chunk): K = {1, 2, 4, 8}[v - 40]; "refill", "chunk" options
@@ -678,6 +703,9 @@ void uvrt_destroy(uvrt_ctx* ctx)
     if (ctx->forkEv) cudaEventDestroy(ctx->forkEv);
     if (ctx->accStream) { cudaStreamSynchronize(ctx->accStream); cudaStreamDestroy(ctx->accStream); }
     if (ctx->dCountsAlt) cudaFree(ctx->dCountsAlt);
+    if (ctx->dQPairs) cudaFree(ctx->dQPairs);
+    if (ctx->dFastGrid) cudaFree(ctx->dFastGrid);
+    if (ctx->dFastStats) cudaFree(ctx->dFastStats);
     if (ctx->dMatrix) cudaFree(ctx->dMatrix);
     if (ctx->dDurations) cudaFree(ctx->dDurations);
     if (ctx->timelineOrigin) cudaEventDestroy(ctx->timelineOrigin);
@@ -781,6 +809,8 @@ static int ensure_scene_buffers(uvrt_ctx* ctx, size_t pairBytes, size_t wtriByte
     }
     return UVRT_OK;
 }
+
+static int fast_prepare(uvrt_ctx* ctx);
 
 static int ensure_stage(uvrt_ctx* ctx, size_t total)
 {
@@ -981,6 +1011,7 @@ static int upload_scene_device(uvrt_ctx* ctx, const void* trisV, int nTris, cons
     ctx->nSlots = (long long)nSlots;
     ctx->depth = (int)s.maxDepth;
     ctx->sceneTame = hSt->tame ? 1 : 0;
+    ctx->sceneNested = hSt->nested ? 1 : 0;
     ctx->rootRef = s.rootIsLeaf ? kLeafFlag : 0u;
     ctx->uploadBytes = (int64_t)(nodeBytes + idxBytes + vertBytes);
     return UVRT_OK;
@@ -1049,9 +1080,9 @@ static int upload_scene_host(uvrt_ctx* ctx, const void* trisV, int nTris, const 
         return nodes[n].triCount > 0 ? (kLeafFlag | (uint32_t)id[n]) : (uint32_t)id[n];
     };
     // every reachable node fills its own record: independent, so spread over the host cores
-    int tameAll = 1;
+    int tameAll = 1, nestedAll = 1;
     const long long nOrder = (long long)order.size();
-#pragma omp parallel for schedule(static) reduction(&& : tameAll) if (nOrder > 4096)
+#pragma omp parallel for schedule(static) reduction(&& : tameAll, nestedAll) if (nOrder > 4096)
     for (long long oi = 0; oi < nOrder; oi++) {
         const uint32_t n = order[oi];
         const HostNode& nd = nodes[n];
@@ -1064,9 +1095,10 @@ static int upload_scene_host(uvrt_ctx* ctx, const void* trisV, int nTris, const 
                 uint32_t tag = t | (k + 1 == nd.triCount ? kLastFlag : 0u);
                 memcpy(&w[3], &tag, 4);
                 // edge1 = v1 - v0, edge2 = v2 - v0 (extend.cl:13): the same fp32 subtractions, hoisted
-                w[4] = v[4] - v[0]; w[5] = v[5] - v[1]; w[6] = v[6] - v[2]; w[7] = 0.0f;
-                w[8] = v[8] - v[0]; w[9] = v[9] - v[1]; w[10] = v[10] - v[2]; w[11] = 0.0f;
-                w[12] = w[13] = w[14] = w[15] = 0.0f;
+                // spare lanes: the leaf's own box, for the exact verification step of the fast extend (uvrt_fast.cuh)
+                w[4] = v[4] - v[0]; w[5] = v[5] - v[1]; w[6] = v[6] - v[2]; w[7] = nd.mn[2];
+                w[8] = v[8] - v[0]; w[9] = v[9] - v[1]; w[10] = v[10] - v[2]; w[11] = nd.mx[2];
+                w[12] = nd.mn[0]; w[13] = nd.mn[1]; w[14] = nd.mx[0]; w[15] = nd.mx[1];
             }
         } else {
             float* p = hp + (size_t)id[n] * 16;
@@ -1080,8 +1112,10 @@ static int upload_scene_host(uvrt_ctx* ctx, const void* trisV, int nTris, const 
                 memcpy(&q[6], &ref, 4);
                 q[7] = 0.0f;
                 // the fast box test needs normal-range coordinates and min <= max on every axis
-                for (int a = 0; a < 3; a++)
+                for (int a = 0; a < 3; a++) {
                     tameAll = tameAll && coord_tame(ch.mn[a]) && coord_tame(ch.mx[a]) && ch.mn[a] <= ch.mx[a];
+                    if (n != 0u) nestedAll = nestedAll && ch.mn[a] >= nd.mn[a] && ch.mx[a] <= nd.mx[a];
+                }
             }
         }
     }
@@ -1100,6 +1134,7 @@ static int upload_scene_host(uvrt_ctx* ctx, const void* trisV, int nTris, const 
     ctx->nSlots = nSlots;
     ctx->depth = depth;
     ctx->sceneTame = tame ? 1 : 0;
+    ctx->sceneNested = nestedAll ? 1 : 0;
     ctx->rootRef = child_ref(0);
     ctx->uploadBytes = (int64_t)total;
     return UVRT_OK;
@@ -1115,8 +1150,35 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* trisV, int nTris, const void* n
     Bind b(ctx);
     // rays of a pipelined launch may still be in flight on the second stream
     if (ctx->genStream) CK(cudaStreamSynchronize(ctx->genStream));
-    return ctx->hostRepack ? upload_scene_host(ctx, trisV, nTris, nodesV, nNodes, triIdx)
-                           : upload_scene_device(ctx, trisV, nTris, nodesV, nNodes, triIdx);
+    int rc = ctx->hostRepack ? upload_scene_host(ctx, trisV, nTris, nodesV, nNodes, triIdx)
+                             : upload_scene_device(ctx, trisV, nTris, nodesV, nNodes, triIdx);
+    if (rc) return rc;
+    return fast_prepare(ctx);
+}
+
+// The node layout of the certified fast extend (uvrt_fast.cuh): quantised copies of the pair records, built on the
+// device from the repacked scene.  Only trees whose boxes are tame and nested qualify; others keep the exact kernel.
+
+static int fast_prepare(uvrt_ctx* ctx)
+{
+    if (ctx->nPairs <= 0 || !ctx->sceneTame || !ctx->sceneNested) return UVRT_OK;
+    if ((size_t)ctx->nPairs > ctx->qpairCap) {
+        uint4* fresh = nullptr;
+        CK(cudaMalloc((void**)&fresh, (size_t)ctx->nPairs * 32));
+        if (ctx->dQPairs) cudaFree(ctx->dQPairs);
+        ctx->dQPairs = fresh;
+        ctx->qpairCap = (size_t)ctx->nPairs;
+    }
+    if (!ctx->dFastGrid) CK(cudaMalloc((void**)&ctx->dFastGrid, sizeof(FastGrid)));
+    if (!ctx->dFastStats) {
+        CK(cudaMalloc((void**)&ctx->dFastStats, sizeof(FastStats)));
+        CK(cudaMemsetAsync(ctx->dFastStats, 0, sizeof(FastStats), ctx->stream));
+    }
+    k_fast_quantize<<<grid_for(ctx->nPairs, 256), 256, 0, ctx->stream>>>(ctx->dPairs, ctx->nPairs, ctx->dQPairs, ctx->dFastGrid);
+    ctx->launches++;
+    CK_LAUNCH("fast_quantize");
+    CK(cudaStreamSynchronize(ctx->stream));
+    return UVRT_OK;
 }
 
 // ---- device BVH build (uvrt_bvh_build.cuh) ----------------------------------------------------------
@@ -1532,7 +1594,10 @@ int uvrt_matrix_begin(uvrt_ctx* ctx, int rows)
     if (need > ctx->matrixCap) {
         int* fresh = nullptr;
         CK(cudaMalloc((void**)&fresh, need * 4));
-        if (ctx->dMatrix) cudaFree(ctx->dMatrix);
+        if (ctx->dQPairs) cudaFree(ctx->dQPairs);
+    if (ctx->dFastGrid) cudaFree(ctx->dFastGrid);
+    if (ctx->dFastStats) cudaFree(ctx->dFastStats);
+    if (ctx->dMatrix) cudaFree(ctx->dMatrix);
         ctx->dMatrix = fresh;
         ctx->matrixCap = need;
     }
@@ -1836,6 +1901,8 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
             ctx->timelineHost0 = host_now_us();
         }
     }
+    else if (!strcmp(key, "fast_check")) ctx->fastCheck = value;
+    else if (!strcmp(key, "fast_cfg")) ctx->fastCfg = value;
     else if (!strcmp(key, "hist_mode")) ctx->histMode = value;
     else if (!strcmp(key, "blocks_per_sm")) ctx->blocksPerSm = value;
     else if (!strcmp(key, "refill")) ctx->refill = value;
@@ -1873,6 +1940,10 @@ int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value)
     else if (!strcmp(key, "hist_mode")) *value = ctx->histMode;
     else if (!strcmp(key, "blocks_per_sm")) *value = ctx->blocksPerSm;
     else if (!strcmp(key, "scene_tame")) *value = ctx->sceneTame;
+    else if (!strcmp(key, "scene_nested")) *value = ctx->sceneNested;
+    else if (!strcmp(key, "fast_ready")) *value = (ctx->nPairs > 0 && ctx->sceneTame && ctx->sceneNested && ctx->dQPairs) ? 1 : 0;
+    else if (!strcmp(key, "fast_check")) *value = ctx->fastCheck;
+    else if (!strcmp(key, "fast_cfg")) *value = ctx->fastCfg;
     else if (!strcmp(key, "experiments")) {
 #ifdef UVRT_EXPERIMENTS
         *value = 1;
@@ -1969,6 +2040,20 @@ int uvrt_elapsed_ms(uvrt_ctx* ctx, int a, int b2, float* ms)
     Bind b(ctx);
     CK(cudaEventSynchronize(ctx->marks[b2]));
     CK(cudaEventElapsedTime(ms, ctx->marks[a], ctx->marks[b2]));
+    return UVRT_OK;
+}
+
+// Counters of the certified fast extend since the last reset: out3 = {rays traced again because the certificate
+// failed, rays not eligible for the fast path, certified rays that differed from the exact traversal ("fast_check")}.
+int uvrt_fast_stats(uvrt_ctx* ctx, unsigned long long* out3, int reset)
+{
+    if (!ctx || !out3) return UVRT_ERR_INVALID;
+    Bind b(ctx);
+    out3[0] = out3[1] = out3[2] = 0;
+    if (!ctx->dFastStats) return UVRT_OK;
+    CK(uvrt_sync(ctx) == UVRT_OK ? cudaSuccess : cudaErrorUnknown);
+    CK(cudaMemcpy(out3, ctx->dFastStats, 24, cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(ctx->dFastStats, 0, sizeof(FastStats)));
     return UVRT_OK;
 }
 

@@ -36,7 +36,7 @@ enum PrepError { PREP_OK = 0, PREP_NODE_RANGE = 1, PREP_TWICE = 2, PREP_LEAF_SPA
 struct Status {                   // one per upload, read back by the host
     uint32_t err, errA, errB, errC;
     uint32_t done, reachable, maxDepth, tame;
-    uint32_t nPairs, nLeaves, rootIsLeaf, pad;
+    uint32_t nPairs, nLeaves, rootIsLeaf, nested;   // nested: every child box lies inside its parent's box
     unsigned long long nSlots;
     uint32_t tail, pad2;
 };
@@ -56,6 +56,7 @@ __global__ void k_prep_init(unsigned long long* __restrict__ queue, Status* __re
 {
     Status z{};
     z.tame = 1;
+    z.nested = 1;
     z.tail = 1;
     *st = z;
     parent[0] = kRootParent;
@@ -163,10 +164,12 @@ __global__ void __launch_bounds__(256) k_prep_emit(const RawNode* __restrict__ n
             const float4 v0 = tris[4ull * t], v1 = tris[4ull * t + 1], v2 = tris[4ull * t + 2];
             float4* w = wtris + 4ull * (sb + k);
             const uint32_t tag = t | (k + 1 == nd.triCount ? kLastBit : 0u);
+            // the spare lanes carry the leaf's own box (every slot of a leaf repeats it) for the exact
+            // verification step of the certified fast extend (uvrt_fast.cuh): min.z | max.z | (min.xy, max.xy)
             w[0] = make_float4(v0.x, v0.y, v0.z, __uint_as_float(tag));
-            w[1] = make_float4(__fsub_rn(v1.x, v0.x), __fsub_rn(v1.y, v0.y), __fsub_rn(v1.z, v0.z), 0.0f);
-            w[2] = make_float4(__fsub_rn(v2.x, v0.x), __fsub_rn(v2.y, v0.y), __fsub_rn(v2.z, v0.z), 0.0f);
-            w[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            w[1] = make_float4(__fsub_rn(v1.x, v0.x), __fsub_rn(v1.y, v0.y), __fsub_rn(v1.z, v0.z), nd.mn[2]);
+            w[2] = make_float4(__fsub_rn(v2.x, v0.x), __fsub_rn(v2.y, v0.y), __fsub_rn(v2.z, v0.z), nd.mx[2]);
+            w[3] = make_float4(nd.mn[0], nd.mn[1], nd.mx[0], nd.mx[1]);
         }
         return;
     }
@@ -185,6 +188,14 @@ __global__ void __launch_bounds__(256) k_prep_emit(const RawNode* __restrict__ n
     for (int k = 0; k < 3; k++)
         tame = tame && coord_tame(a.mn[k]) && coord_tame(a.mx[k]) && a.mn[k] <= a.mx[k] && coord_tame(b.mn[k]) && coord_tame(b.mx[k]) && b.mn[k] <= b.mx[k];
     if (!tame) st->tame = 0;
+    // nested boxes make the exact slab results monotone along a path (uvrt_fast.cuh); the root's own box is never tested
+    if (n != 0u) {
+        bool nested = true;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            nested = nested && a.mn[k] >= nd.mn[k] && a.mx[k] <= nd.mx[k] && b.mn[k] >= nd.mn[k] && b.mx[k] <= nd.mx[k];
+        if (!nested) st->nested = 0;
+    }
 }
 
 } // namespace uvrt_prep

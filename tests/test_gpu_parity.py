@@ -17,7 +17,7 @@ from conftest import lange_pos0
 pytestmark = pytest.mark.gpu
 
 DOSE_RTOL = 1e-3          # tolerance stated by BASELINE.json north_star
-SIMPLE_VARIANTS = [0, 1, 2]
+SIMPLE_VARIANTS = [0, 1, 2, 50, 51]      # 50 / 51: the certified fast extend (csrc/uvrt_fast.cuh)
 PERSIST_VARIANTS = [10, 11, 12, 16, 17, 19, 20, 22, 23, 24]
 
 
@@ -132,7 +132,7 @@ def test_full_size_launch_matches_golden(uv, ctx, room, golden):
         assert rays[int(i)].tobytes().hex() == hexs
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 11, 23])
+@pytest.mark.parametrize("variant", [0, 1, 2, 50, 51, 11, 23])
 @pytest.mark.parametrize("binned", [0, 1])
 def test_extend_degenerate_rays(uv, ctx, room, variant, binned):
     """Axis-parallel directions (division by zero, 0/0 = NaN on slab planes), origins outside the
@@ -908,3 +908,88 @@ def test_host_seed_chain_equals_device_seed_chain(uv, ctx, room):
         for k, lp in enumerate(lps):
             seed = int(H.uvrt_host_seed_after_launch(lp[0], lp[1], lp[2], f32(p.lightLength), seed))
             assert seed == int(chain[k + 1])
+
+
+@pytest.mark.parametrize("variant", [50, 51])
+def test_fast_extend_default_run_matches_reference_golden(uv, room, variant):
+    """The certified fast extend on BASELINE configs[1] at full size (335,544,240 rays): every map of the run hashes
+    to the golden of the reference's own compiled sources, i.e. not one ray of the run got another triangle or
+    distance; and with "fast_check" (every ray also traced in reference order) no certified ray disagrees."""
+    g = _run_golden("route")
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_mesh("testroomopt")
+    sim.init("route")
+    c = sim.ctx
+    assert c.get_option("scene_nested") == 1 and c.get_option("fast_ready") == 1
+    c.set_option("extend_variant", variant)
+    c.fast_stats(reset=True)
+    dose = sim.run()
+    a = g["after_iteration"][9]
+    got = (f"{T.fnv(c.read(uv.BUF.SUM)):016x}", f"{T.fnv(c.read(uv.BUF.MAX)):016x}", f"{T.fnv(dose):016x}", f"{T.fnv(c.read(uv.BUF.COLOR)):016x}")
+    assert got == (a["fnv_photonMap"], a["fnv_maxPhotonMap"], a["fnv_dose"], a["fnv_color"])
+    st = c.fast_stats(reset=True)
+    assert st["ineligible"] < 335_544_240 * 1e-4          # axis-parallel rays and the like
+    assert st["cert_fallbacks"] < 335_544_240 * 1e-3      # two surfaces within 2^-12: re-traced in reference order
+    # one pass with every ray traced both ways
+    c.set_option("fast_check", 1)
+    sim.set_params(maxIterations=1)
+    sim.set_seed(0)
+    sim.run()
+    st = c.fast_stats(reset=True)
+    assert st["check_mismatches"] == 0, st
+    assert f"{T.fnv(sim.read_dose()):016x}" == g["after_iteration"][0]["fnv_dose"]
+    sim.close()
+
+
+def test_fast_extend_soup_check_mode(uv):
+    """The 1 M-triangle soup (deep, incoherent traversal) through both fast variants with every ray traced both
+    ways: no certified ray disagrees with the reference order, and the counts equal the golden."""
+    import json
+    import sys as _sys
+    _sys.path.insert(0, T.ROOT + "/tools")
+    from soup import make_soup, soup_route
+    g = json.load(open(os.path.join(T.ROOT, "tests", "golden", "soup.json")))["scenes"]["1000000"]["launch"]["5:3"]
+    c = uv.Context(0)
+    tris, nodes, tri_idx = c.build_bvh(make_soup(1_000_000))
+    c.upload_scene(tris, nodes, tri_idx)
+    assert c.get_option("fast_ready") == 1
+    x, z, _ = soup_route()[5]
+    lp = (np.float32(x), np.float32(0.5), np.float32(z))
+    for variant in (50, 51):
+        c.set_option("extend_variant", variant)
+        c.set_option("fast_check", 1)
+        c.fast_stats(reset=True)
+        c.reset(False)
+        c.trace_counts(lp, 1.0, 0, g["rays"], g["seed_in"])
+        counts = c.read(uv.BUF.COUNTS)
+        rays = c.read(uv.BUF.RAYS, g["rays"])
+        st = c.fast_stats(reset=True)
+        assert st["check_mismatches"] == 0, (variant, st)
+        assert f"{T.fnv(counts):016x}" == g["fnv_counts"]
+        assert f"{int(T.oracle().orc_fnv_hits(T.ptr(rays), g['rays'])):016x}" == g["fnv_hits"]
+        c.set_option("fast_check", 0)
+        c.reset(False)
+        c.trace_counts(lp, 1.0, 0, g["rays"], g["seed_in"])
+        assert f"{T.fnv(c.read(uv.BUF.COUNTS)):016x}" == g["fnv_counts"]
+    c.close()
+
+
+def test_fast_extend_falls_back_on_scenes_it_cannot_serve(uv, room):
+    """Boxes that are not nested (a hand-made tree) or coordinates outside the tame range: variant 50 must take the
+    exact kernel and still give the exact kernel's answer."""
+    tris, nodes, tri_idx, floor = room
+    bad = nodes.copy()
+    k = int(np.flatnonzero(bad["triCount"] == 0)[5])
+    bad[k]["min"] = bad[k]["min"] + np.float32(0.01)          # the node's box no longer contains its children
+    c = uv.Context(0)
+    c.upload_scene(tris, bad, tri_idx)
+    assert c.get_option("scene_nested") == 0 and c.get_option("fast_ready") == 0
+    lp = lange_pos0(floor)
+    out = []
+    for variant in (2, 50):
+        c.set_option("extend_variant", variant)
+        c.reset(True)
+        c.trace_counts(lp, 1.0, 0, 200_000, 5)
+        out.append((c.read(uv.BUF.RAYS, 200_000).tobytes(), c.read(uv.BUF.COUNTS).tobytes()))
+    assert out[0] == out[1]
+    c.close()
