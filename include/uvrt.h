@@ -93,7 +93,11 @@ int uvrt_upload_scene(uvrt_ctx* ctx, const void* tris, int nTris, const void* no
  * numbering and triIdx order (bit-identical to host/bvh.cpp).  tris: nTris x 64 B (host); the
  * centroid lanes are written back when trisOut != NULL (the builder computes them, bvh.cpp:23).
  * nodesOut: nodeCapacity x 32 B (host; 2*nTris + 64 is always enough); triIdxOut: nTris x u32.
- * *nodesUsed = highest used node index + 1.  Synchronises.  Independent of the uploaded scene. */
+ * *nodesUsed = highest used node index + 1.  Synchronises.  Independent of the uploaded scene.
+ * One caveat to "bit-identical": where a box or centroid extremum is attained by both -0.0 and +0.0 the host
+ * builder keeps the zero it meets first in triangle order (p < lo ? p : lo), the device reduction the smaller
+ * encoding (-0.0 for a minimum, +0.0 for a maximum).  Topology, triIdx and every non-zero bound are identical, and
+ * no comparison or quotient of the traversal can tell the two zeros apart (a - o is the same number either way). */
 int uvrt_build_bvh(uvrt_ctx* ctx, const void* tris, int nTris, void* nodesOut, int nodeCapacity,
                    uint32_t* triIdxOut, uint32_t* nodesUsed, void* trisOut);
 
@@ -166,11 +170,12 @@ int uvrt_matrix_fold(uvrt_ctx* ctx, const float* durations, int rows, int reduce
 /* Options (defaults are the measured best; everything else exists for A/B runs, see DESIGN.md section 4 and
  * profiles/r1_sweeps.md):
  *   "extend_variant"  kernel selection: 0/1/2 one thread per ray with IEEE / two-step / one-step (default) slab
- *                     division; 50 / 51 the certified fast extend (csrc/uvrt_fast.cuh: conservative inner-node
- *                     tests on 32-byte quantised / 64-byte fp32 node pairs, exact verification of every accepted
- *                     hit, rays without a certificate re-traced in reference order; "fast_check" = 1 traces every
- *                     ray both ways and counts disagreements, "fast_cfg" selects the register budget; read only:
- *                     "scene_nested", "fast_ready").  Builds with -DUVRT_EXPERIMENTS (`make EXPERIMENTS=1`, read-only option
+ *                     division; 50 the certified fast extend (csrc/uvrt_fast.cuh: conservative inner-node tests
+ *                     on 32-byte quantised node pairs, the winner verified with the reference's exact slab test,
+ *                     rays without a certificate re-traced in reference order -- same bits as 0/1/2).  -1 (default)
+ *                     picks per scene: 2 for trees that live in the caches, 50 from 400 k inner nodes up.
+ *                     "fast_check" = 1 traces every ray both ways and counts disagreements (uvrt_fast_stats),
+ *                     "fast_cfg" selects the register budget; read only: "scene_nested", "fast_ready".  Builds with -DUVRT_EXPERIMENTS (`make EXPERIMENTS=1`, read-only option
  *                     "experiments") also carry the rejected variants of profiles/r1_sweeps.md: 10..24 persistent
  *                     warps with a global queue, 40..43 chunk-persistent warps
  *   "bin_rays"        1 (default): counting sort of the ray queue by direction / origin cell before extend;
@@ -207,7 +212,7 @@ int64_t uvrt_scene_upload_bytes(const uvrt_ctx* ctx);
 /* Traversal statistics of the repacked scene: inner nodes, leaves, depth, stack bound. */
 int uvrt_scene_info(uvrt_ctx* ctx, int* innerNodes, int* leaves, int* depth, int* stackEntries);
 
-/* Certified fast extend ("extend_variant" 50 / 51, csrc/uvrt_fast.cuh): counters since the last reset.
+/* Certified fast extend ("extend_variant" 50, csrc/uvrt_fast.cuh): counters since the last reset.
  * out3 = {rays traced again in reference order because their certificate failed, rays not eligible for the fast
  * path (not tame, origin far outside the scene, a hit already recorded), certified rays whose answer differed
  * from the reference-order traversal -- counted only with option "fast_check" = 1, which traces every ray both

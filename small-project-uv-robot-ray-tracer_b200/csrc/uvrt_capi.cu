@@ -302,6 +302,16 @@ struct StageTimer {
     }
 };
 
+// UVRT_DEBUG_ERRORS=1: report a CUDA error that is still pending when an entry point returns (an ignored return
+// value somewhere inside it), instead of letting the next unrelated launch check trip over it.
+void debug_pending_error(const char* where)
+{
+    static const bool on = getenv("UVRT_DEBUG_ERRORS") != nullptr;
+    if (!on) return;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) fprintf(stderr, "[uvrt debug] CUDA error pending after %s: %s\n", where, cudaGetErrorString(e));
+}
+
 // One per C-ABI entry point that does work: NVTX range + (with "timeline") a host-side record of the call.
 struct ApiScope {
     uvrt_ctx* ctx;
@@ -316,6 +326,7 @@ struct ApiScope {
     {
         nvtxRangePop();
         if (ctx && ctx->timeline) ctx->apiLog.push_back({name, t0, host_now_us() - ctx->timelineHost0});
+        debug_pending_error(name);
     }
 };
 
@@ -372,6 +383,9 @@ inline bool wants_binning(const uvrt_ctx* ctx, long long nRays)
     return ctx->binRays && nRays >= kMinRaysForBinning && ctx->nPairs >= kMinPairsForBinning;
 }
 
+inline bool fast_usable(const uvrt_ctx* ctx) { return ctx->nPairs > 0 && ctx->sceneTame && ctx->sceneNested && ctx->dQPairs != nullptr; }
+inline int default_variant(const uvrt_ctx* ctx) { return fast_usable(ctx) && ctx->nPairs >= kFastMinPairs ? 50 : kDefaultVariant; }
+
 inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
 // ---- extend dispatch ---------------------------------------------------------------------------
@@ -382,6 +396,12 @@ inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block 
 //   10 + 3*k + d  persistent, K = {1, 2, 4, 8, inf}[k], d = {IEEE, M2, M1}
 constexpr int kStack = 64;
 constexpr int kDefaultVariant = 2;   // one thread per ray, one-step shared-reciprocal division (proven exact)
+// "extend_variant" -1 (the default) picks per scene: the exact kernel for trees that live in the caches (rooms: the
+// certified fast kernel issues as many instructions there and gains nothing, profiles/r2_fast_extend.md), the certified
+// fast kernel for trees that do not (its 32-byte node records halve the traffic and the latency per visit: 1.3-1.65x on
+// the 1 M / 10 M-triangle soups).  Both give the same bits.
+constexpr int kFastMinPairs = 400000;   // 400 k inner nodes = 25.6 MB of exact node records: beyond L1 + a good part of L2
+inline int default_variant(const uvrt_ctx* ctx);
 
 template <int DIV, int THREADS, int MINB>
 void launch_simple_cfg(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
@@ -550,7 +570,7 @@ int bin_finish(uvrt_ctx* ctx, long long nRays, cudaStream_t stream)
 
 int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
-    int v = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
+    int v = ctx->extendVariant < 0 ? default_variant(ctx) : ctx->extendVariant;
     if (v == 0) launch_simple<DIV_IEEE>(ctx, nRays, perm);
     else if (v == 1) launch_simple<DIV_MARKSTEIN2>(ctx, nRays, perm);
     else if (v == 2 && ctx->fetchMode == 3 && ctx->simpleCfg == 1) launch_simple_fetch<3>(ctx, nRays, perm);
@@ -561,19 +581,20 @@ int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     else if (v == 2 && ctx->fetchMode == 5 && perm) launch_simple_fetch<5>(ctx, nRays, perm);
 #endif
     else if (v == 2) launch_simple<DIV_MARKSTEIN1>(ctx, nRays, perm);
-    else if (v == 50 || v == 51) {
-        // certified fast extend (50: 32-byte quantised node pairs, 51: conservative fp32 test on the exact kernel's pairs);
-        // scenes it cannot serve (boxes not tame / not nested, a single leaf) take the exact kernel
-        if (ctx->nPairs > 0 && ctx->sceneTame && ctx->sceneNested && ctx->dQPairs && nRays <= 0x7fffffffLL) {
-#define UVRT_FAST_LAUNCH(MINB, NODES)                                                                                      \
-    k_extend_fast<kStack, 128, MINB, NODES><<<grid_for(nRays, 128), 128, 0, ctx->xStream>>>(                                \
-        ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->dQPairs, ctx->dFastGrid, (uint32_t)nRays, perm, ctx->dFastStats, ctx->fastCheck)
-            // "fast_cfg": 0 = at most 48 registers (40 resident warps per SM, a few spills), 1 = at most 64 (32 warps, none)
-            if (v == 50 && ctx->fastCfg == 0) UVRT_FAST_LAUNCH(10, 0);
-            else if (v == 50) UVRT_FAST_LAUNCH(8, 0);
-            else if (ctx->fastCfg == 0) UVRT_FAST_LAUNCH(10, 1);
-            else UVRT_FAST_LAUNCH(8, 1);
-#undef UVRT_FAST_LAUNCH
+    else if (v == 50) {
+        // certified fast extend (uvrt_fast.cuh); scenes it cannot serve (boxes not tame / not nested, a single leaf)
+        // take the exact kernel
+        if (fast_usable(ctx) && nRays <= 0x7fffffffLL) {
+            // "fast_cfg": 0 = at most 48 registers (40 resident warps per SM), 1 = at most 64 (32 warps), 2 = at most 40 (48 warps)
+            if (ctx->fastCfg == 1)
+                k_extend_fast<kStack, 128, 8><<<grid_for(nRays, 128), 128, 0, ctx->xStream>>>(
+                    ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->dQPairs, ctx->dFastGrid, (uint32_t)nRays, perm, ctx->dFastStats, ctx->fastCheck);
+            else if (ctx->fastCfg == 2)
+                k_extend_fast<kStack, 128, 12><<<grid_for(nRays, 128), 128, 0, ctx->xStream>>>(
+                    ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->dQPairs, ctx->dFastGrid, (uint32_t)nRays, perm, ctx->dFastStats, ctx->fastCheck);
+            else
+                k_extend_fast<kStack, 128, 10><<<grid_for(nRays, 128), 128, 0, ctx->xStream>>>(
+                    ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->dQPairs, ctx->dFastGrid, (uint32_t)nRays, perm, ctx->dFastStats, ctx->fastCheck);
         } else
             launch_simple_fetch<3>(ctx, nRays, perm);
     }
@@ -687,6 +708,7 @@ void uvrt_destroy(uvrt_ctx* ctx)
 {
     if (!ctx) return;
     Bind b(ctx);
+    debug_pending_error("(entering uvrt_destroy)");
     if (ctx->genStream) cudaStreamSynchronize(ctx->genStream);
     for (int k = 0; k < 2; k++) if (ctx->extStream[k]) cudaStreamSynchronize(ctx->extStream[k]);
     cudaStreamSynchronize(ctx->stream);
@@ -730,6 +752,7 @@ void uvrt_destroy(uvrt_ctx* ctx)
     for (auto e : ctx->freeEvents) cudaEventDestroy(e);
     for (auto e : ctx->marks) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
+    debug_pending_error("uvrt_destroy");
     delete ctx;
 }
 
@@ -1509,7 +1532,7 @@ int uvrt_trace(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, f
     if (!ctx->nTris) return fail(ctx, UVRT_ERR_NO_SCENE, "%s: no scene uploaded", __func__);
     ApiScope api_(ctx, "uvrt_trace");
     const bool foreign = ctx->mainForeign;
-    const int variant = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
+    const int variant = ctx->extendVariant < 0 ? default_variant(ctx) : ctx->extendVariant;
     const bool sharedQueue = variant >= 10 && variant < 25;   // variant B's global queue head is one per context
     // counts left behind by uvrt_extend / uvrt_trace_counts belong to this launch's accumulate as well: they sit
     // in the primary buffer, so this launch must use it too
@@ -1594,10 +1617,7 @@ int uvrt_matrix_begin(uvrt_ctx* ctx, int rows)
     if (need > ctx->matrixCap) {
         int* fresh = nullptr;
         CK(cudaMalloc((void**)&fresh, need * 4));
-        if (ctx->dQPairs) cudaFree(ctx->dQPairs);
-    if (ctx->dFastGrid) cudaFree(ctx->dFastGrid);
-    if (ctx->dFastStats) cudaFree(ctx->dFastStats);
-    if (ctx->dMatrix) cudaFree(ctx->dMatrix);
+        if (ctx->dMatrix) cudaFree(ctx->dMatrix);
         ctx->dMatrix = fresh;
         ctx->matrixCap = need;
     }
@@ -1934,14 +1954,14 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
 int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value)
 {
     if (!ctx || !key || !value) return UVRT_ERR_INVALID;
-    if (!strcmp(key, "extend_variant")) *value = ctx->extendVariant < 0 ? kDefaultVariant : ctx->extendVariant;
+    if (!strcmp(key, "extend_variant")) *value = ctx->extendVariant < 0 ? default_variant(ctx) : ctx->extendVariant;
     else if (!strcmp(key, "stage_timing")) *value = ctx->stageTiming;
     else if (!strcmp(key, "timeline")) *value = ctx->timeline;
     else if (!strcmp(key, "hist_mode")) *value = ctx->histMode;
     else if (!strcmp(key, "blocks_per_sm")) *value = ctx->blocksPerSm;
     else if (!strcmp(key, "scene_tame")) *value = ctx->sceneTame;
     else if (!strcmp(key, "scene_nested")) *value = ctx->sceneNested;
-    else if (!strcmp(key, "fast_ready")) *value = (ctx->nPairs > 0 && ctx->sceneTame && ctx->sceneNested && ctx->dQPairs) ? 1 : 0;
+    else if (!strcmp(key, "fast_ready")) *value = fast_usable(ctx) ? 1 : 0;
     else if (!strcmp(key, "fast_check")) *value = ctx->fastCheck;
     else if (!strcmp(key, "fast_cfg")) *value = ctx->fastCfg;
     else if (!strcmp(key, "experiments")) {

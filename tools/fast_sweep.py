@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--positions", default="0,5,11")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--check", action="store_true")
-    ap.add_argument("--variants", default="2,50,51")
+    ap.add_argument("--variants", default="2,50")
     args = ap.parse_args()
     f32 = np.float32
     if args.scene == "room":
@@ -56,7 +56,7 @@ def main():
         lp = lamps[pi]
         ref = None
         for v in [int(x) for x in args.variants.split(",")]:
-            for cfg in ((0, 1) if v >= 50 else (0,)):
+            for cfg in ((0, 1, 2) if v >= 50 else (0,)):
                 c.set_option("extend_variant", v)
                 c.set_option("fast_cfg", cfg)
                 c.set_option("fast_check", 0)
