@@ -383,6 +383,12 @@ inline bool wants_binning(const uvrt_ctx* ctx, long long nRays)
     return ctx->binRays && nRays >= kMinRaysForBinning && ctx->nPairs >= kMinPairsForBinning;
 }
 
+constexpr int kDefaultVariant = 2;   // one thread per ray, one-step shared-reciprocal division (proven exact)
+// "extend_variant" -1 (the default) picks per scene: the exact kernel for trees that live in the caches (rooms: the
+// certified fast kernel issues as many instructions there and gains nothing, profiles/r2_fast_extend.md), the certified
+// fast kernel for trees that do not (its 32-byte node records halve the traffic and the latency per visit: 1.3-1.65x on
+// the 1 M / 10 M-triangle soups).  Both give the same bits.
+constexpr int kFastMinPairs = 400000;   // 400 k inner nodes = 25.6 MB of exact node records: beyond L1 + a good part of L2
 inline bool fast_usable(const uvrt_ctx* ctx) { return ctx->nPairs > 0 && ctx->sceneTame && ctx->sceneNested && ctx->dQPairs != nullptr; }
 inline int default_variant(const uvrt_ctx* ctx) { return fast_usable(ctx) && ctx->nPairs >= kFastMinPairs ? 50 : kDefaultVariant; }
 
@@ -395,13 +401,7 @@ inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block 
 //   2  simple / Markstein one-step
 //   10 + 3*k + d  persistent, K = {1, 2, 4, 8, inf}[k], d = {IEEE, M2, M1}
 constexpr int kStack = 64;
-constexpr int kDefaultVariant = 2;   // one thread per ray, one-step shared-reciprocal division (proven exact)
-// "extend_variant" -1 (the default) picks per scene: the exact kernel for trees that live in the caches (rooms: the
-// certified fast kernel issues as many instructions there and gains nothing, profiles/r2_fast_extend.md), the certified
-// fast kernel for trees that do not (its 32-byte node records halve the traffic and the latency per visit: 1.3-1.65x on
-// the 1 M / 10 M-triangle soups).  Both give the same bits.
-constexpr int kFastMinPairs = 400000;   // 400 k inner nodes = 25.6 MB of exact node records: beyond L1 + a good part of L2
-inline int default_variant(const uvrt_ctx* ctx);
+
 
 template <int DIV, int THREADS, int MINB>
 void launch_simple_cfg(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
