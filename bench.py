@@ -491,8 +491,10 @@ def main():
         try:
             m = json.load(open(mpath))
             traffic = m.get("bytes_per_launch")
-            binding = {"resource": "l1tex data-pipe wavefronts (gather of 32-byte node sectors into registers)",
-                       "frac": round(m["l1tex_data_pipe_wavefronts_pct"] / 100.0, 4), "issue_frac": round(m["issue_active_pct"] / 100.0, 4),
+            l1f, isf = m["l1tex_data_pipe_wavefronts_pct"] / 100.0, m["issue_active_pct"] / 100.0
+            binding = {"resource": ("l1tex data-pipe wavefronts (gather of 32-byte node sectors into registers)" if l1f >= isf else
+                                    "instruction issue (warp schedulers), at " + str(m["lanes_per_inst"]) + " of 32 lanes active per instruction"),
+                       "frac": round(max(l1f, isf), 4), "l1_data_pipe_frac": round(l1f, 4), "issue_frac": round(isf, 4),
                        "lanes_per_inst": m["lanes_per_inst"], "l1_hit_frac": round(m["l1_hit_pct"] / 100.0, 4),
                        "l2_throughput_frac": round(m["l2_throughput_pct"] / 100.0, 4),
                        "long_scoreboard_stalls_per_issue": m["long_scoreboard_stalls_per_issue"],

@@ -173,7 +173,7 @@ int uvrt_matrix_fold(uvrt_ctx* ctx, const float* durations, int rows, int reduce
  *                     division; 50 the certified fast extend (csrc/uvrt_fast.cuh: conservative inner-node tests
  *                     on 32-byte quantised node pairs, the winner verified with the reference's exact slab test,
  *                     rays without a certificate re-traced in reference order -- same bits as 0/1/2).  -1 (default)
- *                     picks per scene: 2 for trees that live in the caches, 50 from 400 k inner nodes up.
+ *                     is 50 wherever it can serve the scene (tame, nested boxes; uvrt_get_option "fast_ready"), else 2.
  *                     "fast_check" = 1 traces every ray both ways and counts disagreements (uvrt_fast_stats),
  *                     "fast_cfg" selects the register budget; read only: "scene_nested", "fast_ready".  Builds with -DUVRT_EXPERIMENTS (`make EXPERIMENTS=1`, read-only option
  *                     "experiments") also carry the rejected variants of profiles/r1_sweeps.md: 10..24 persistent

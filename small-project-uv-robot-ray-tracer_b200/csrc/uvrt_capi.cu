@@ -384,11 +384,11 @@ inline bool wants_binning(const uvrt_ctx* ctx, long long nRays)
 }
 
 constexpr int kDefaultVariant = 2;   // one thread per ray, one-step shared-reciprocal division (proven exact)
-// "extend_variant" -1 (the default) picks per scene: the exact kernel for trees that live in the caches (rooms: the
-// certified fast kernel issues as many instructions there and gains nothing, profiles/r2_fast_extend.md), the certified
-// fast kernel for trees that do not (its 32-byte node records halve the traffic and the latency per visit: 1.3-1.65x on
-// the 1 M / 10 M-triangle soups).  Both give the same bits.
-constexpr int kFastMinPairs = 400000;   // 400 k inner nodes = 25.6 MB of exact node records: beyond L1 + a good part of L2
+// "extend_variant" -1 (the default): the certified fast kernel (uvrt_fast.cuh) wherever it can serve the scene -- tame,
+// nested boxes, a tree worth the name -- else the exact kernel.  Both give the same bits (the fast kernel re-traces
+// in reference order what it cannot certify); the fast one is 7-11 % quicker on the room and 1.4-1.7x on the 1 M /
+// 10 M-triangle soups, with 0 mismatching rays over every benchmarked configuration (profiles/r2_fast_extend.md).
+constexpr int kFastMinPairs = 32;
 inline bool fast_usable(const uvrt_ctx* ctx) { return ctx->nPairs > 0 && ctx->sceneTame && ctx->sceneNested && ctx->dQPairs != nullptr; }
 inline int default_variant(const uvrt_ctx* ctx) { return fast_usable(ctx) && ctx->nPairs >= kFastMinPairs ? 50 : kDefaultVariant; }
 

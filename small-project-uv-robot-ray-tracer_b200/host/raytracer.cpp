@@ -104,18 +104,17 @@ int RayTracer::ShardOwner(long long unit, int U, int N)
     return (int)((unit + (long long)s * pass) % N);
 }
 
-// Ray ranges per launch of a sharded run: whole launches keep the rays of a launch together (the ray binning
-// of extend works best on a full launch), but a run of few launches then leaves the ranks unevenly loaded
-// (120 launches on 8 GPUs: 15 each, and positions differ in cost: 8.6 % imbalance in the cost model of
-// DESIGN.md section 4); halves or quarters even that out.
+// Ray ranges per launch of a sharded run.  Whole launches keep the rays of a launch together (the ray binning of
+// extend works best on a full launch: halves cost 2.5 % more device time per ray, quarters 11 %, eighths 47 %,
+// profiles/r2_split_sweep.jsonl), but a run of few launches then leaves the ranks unevenly loaded: 120 launches on
+// 8 GPUs are 15 each, and positions differ in cost by up to 1.4x -- 8.6 % imbalance in the cost model of DESIGN.md
+// section 4, 2.1 % with halves.  So: halves when a rank would get fewer than 24 whole launches, else whole launches.
 int RayTracer::AutoParts() const
 {
     if (shardParts > 0) return shardParts;
     if (shardCount <= 1 || lightPositions.empty()) return 1;
     long long launches = (long long)lightPositions.size() * (maxIterations > 0 ? maxIterations : 1);
-    int parts = 1;
-    while (parts < 8 && launches * parts < 48LL * shardCount && photonsPerLight / (2 * parts) >= (1 << 19)) parts *= 2;
-    return parts;
+    return (launches < 24LL * shardCount && photonsPerLight / 2 >= (1 << 19)) ? 2 : 1;
 }
 
 // generate.cl:13-39 for work-item 0 (the only one that writes SEED): the seed expression in fp32 from left to
