@@ -152,10 +152,12 @@ void RayTracer::BeginWindow()
     const long long L = (long long)lightPositions.size();
     long long remaining = L;
     if (launchCounter % L == 0 && maxIterations > currIterations) remaining = (long long)(maxIterations - currIterations) * L;
-    // one int32 row per launch: at most 256 MiB of rows at a time
-    long long maxRows = (256LL << 20) / (4LL * (mesh->triangleCount > 0 ? mesh->triangleCount : 1));
+    // one int32 row per launch: at most 64 MiB and 256 rows at a time -- a window is one allocation and one all-reduce,
+    // and both should have the size they had in the caller's warm-up passes (a 268 MB first-time window cost 1.2 s
+    // of allocator and NCCL set-up in the middle of a timed run, profiles/r2_bench_n8_first.json)
+    long long maxRows = (64LL << 20) / (4LL * (mesh->triangleCount > 0 ? mesh->triangleCount : 1));
     if (maxRows < 1) maxRows = 1;
-    if (maxRows > 4096) maxRows = 4096;
+    if (maxRows > 256) maxRows = 256;
     windowRows = (int)(remaining < maxRows ? remaining : maxRows);
     windowFill = 0;
     windowDurations.assign((size_t)windowRows, 0.0f);
