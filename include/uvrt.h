@@ -149,6 +149,12 @@ int uvrt_reduce(uvrt_ctx* ctx);
 /* Sum of UVRT_BUF_COUNTS over all ranks (in place). */
 int uvrt_reduce_counts(uvrt_ctx* ctx);
 
+/* Relative cost of a launch at a lamp position, for sharing launches between GPUs evenly: inner-node visits and
+ * triangle tests per ray over the first nRays rays of the launch (reference-order traversal with counters).
+ * Deterministic: every rank gets the same numbers.  Synchronises; does not touch rays, counts or maps. */
+int uvrt_probe_cost(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, uint32_t seedIn, int nRays,
+                    double* innerVisitsPerRay, double* triangleTestsPerRay);
+
 /* Count matrix: the exchange format of runs whose launches are shared between GPUs, whole or cut into ray
  * ranges.  accumulate.cl:4-14 folds every launch's integer counts into an f64 sum and an
  * f64 per-launch maximum, so per-GPU f64 maps can only be combined exactly when no launch is split and the

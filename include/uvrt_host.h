@@ -88,6 +88,11 @@ int uvrt_sim_read_dose(uvrt_sim* sim, float* dst, int capacity);
 int uvrt_sim_set_shard(uvrt_sim* sim, int rank, int count);
 int uvrt_sim_set_shard_parts(uvrt_sim* sim, int parts);
 int uvrt_sim_shard_parts(const uvrt_sim* sim);           /* the value in effect for the next run */
+/* parts == 0 and cost-aware sharing on (default): ResetDosageMap probes the relative cost of every lamp position
+ * (uvrt_probe_cost; deterministic, identical on every rank) and deals the whole launches of the run longest-first to
+ * the least loaded rank (uvrt_host_plan_shards); off: the rotation of uvrt_host_shard_owner with halves for short runs. */
+int uvrt_sim_set_cost_aware(uvrt_sim* sim, int on);
+int uvrt_host_plan_shards(const double* launchCost, int launches, int ranks, int* ownerOut);
 int uvrt_sim_reduce(uvrt_sim* sim);
 /* The rank that traces unit `unit` (counted over the whole run) of a run with `unitsPerPass` units per pass on
  * `ranks` GPUs (RayTracer::ShardOwner). */

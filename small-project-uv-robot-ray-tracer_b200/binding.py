@@ -103,6 +103,7 @@ def lib():
         "uvrt_comm_init": (i, [vp, vp, i, i]),
         "uvrt_reduce": (i, [vp]),
         "uvrt_reduce_counts": (i, [vp]),
+        "uvrt_probe_cost": (i, [vp, f, f, f, f, u32, i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "uvrt_matrix_begin": (i, [vp, i]),
         "uvrt_trace_row": (i, [vp, i, f, f, f, f, i64, i64, u32]),
         "uvrt_matrix_fold": (i, [vp, vp, i, i]),
@@ -168,6 +169,8 @@ def host():
         "uvrt_sim_set_shard": (i, [vp, i, i]),
         "uvrt_sim_set_shard_parts": (i, [vp, i]),
         "uvrt_sim_shard_parts": (i, [vp]),
+        "uvrt_sim_set_cost_aware": (i, [vp, i]),
+        "uvrt_host_plan_shards": (i, [vp, i, i, vp]),
         "uvrt_sim_set_seed": (i, [vp, C.c_uint32]),
         "uvrt_host_seed_after_launch": (C.c_uint32, [f, f, f, f, C.c_uint32]),
         "uvrt_host_shard_owner": (i, [C.c_longlong, i, i]),
@@ -364,6 +367,11 @@ class Context:
     def reduce_counts(self):
         self.check(self.L.uvrt_reduce_counts(self.h))
 
+    def probe_cost(self, lp, light_length, seed_in=0, n_rays=8192):
+        a, b = C.c_double(), C.c_double()
+        self.check(self.L.uvrt_probe_cost(self.h, lp[0], lp[1], lp[2], light_length, seed_in, n_rays, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def matrix_begin(self, rows):
         self.check(self.L.uvrt_matrix_begin(self.h, rows))
 
@@ -528,6 +536,9 @@ class Sim:
 
     def set_shard_parts(self, parts):
         self.check(self.H.uvrt_sim_set_shard_parts(self.h, parts))
+
+    def set_cost_aware(self, on=True):
+        self.check(self.H.uvrt_sim_set_cost_aware(self.h, int(on)))
 
     def shard_parts(self):
         return int(self.H.uvrt_sim_shard_parts(self.h))

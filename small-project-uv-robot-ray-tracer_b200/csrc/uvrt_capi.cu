@@ -1601,6 +1601,27 @@ int uvrt_trace(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, f
     return UVRT_OK;
 }
 
+// Relative cost of a launch at a lamp position: inner-node visits and triangle tests per ray over the first
+// nRays rays of the launch, traversed in reference order (k_probe_cost).  Deterministic, so every rank of a sharded
+// run computes the same numbers and deals the launches alike without an exchange.  Synchronises.
+int uvrt_probe_cost(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLength, uint32_t seedIn, int nRays, double* innerPerRay,
+                    double* testsPerRay)
+{
+    NEED_SCENE();
+    if (nRays < 1 || nRays > (1 << 24)) return fail(ctx, UVRT_ERR_INVALID, "probe_cost: nRays = %d", nRays);
+    unsigned long long* d = (unsigned long long*)ctx->dQueue;      // 256 bytes of scratch owned by the context
+    CK(cudaMemsetAsync(d + 8, 0, 16, ctx->stream));
+    k_probe_cost<<<grid_for(nRays, 128), 128, 0, ctx->stream>>>(ctx->dPairs, ctx->dWtris, ctx->rootRef, nRays, lx, ly, lz, lightLength, seedIn, d + 8);
+    ctx->launches++;
+    CK_LAUNCH("probe_cost");
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, d + 8, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (innerPerRay) *innerPerRay = (double)h[0] / nRays;
+    if (testsPerRay) *testsPerRay = (double)h[1] / nRays;
+    return UVRT_OK;
+}
+
 // ---- count matrix: launches of a run write their integer counts to one row each -----------------------
 // For runs whose launches are shared between GPUs (whole launches or ray ranges of a launch): every rank
 // traces its rays of launch k into row k, ONE all-reduce sums the integer rows, and the fold replays

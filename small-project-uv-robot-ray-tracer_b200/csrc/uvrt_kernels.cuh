@@ -622,6 +622,67 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_extend_simple(int* __res
 namespace uvrt {
 #endif
 
+// ---- cost probe (work sharing between GPUs) ------------------------------------------------------
+// The first nRays rays of a launch at one lamp position, traversed in reference order with counters: inner-node
+// visits and triangle tests per ray say how expensive the position is relative to the others (they differ by up to
+// 1.4x on the room).  Every rank runs the same deterministic probe, so all ranks deal the launches alike without
+// an exchange (RayTracer::PlanShards).  out[0] += inner visits, out[1] += triangle tests.
+__global__ void __launch_bounds__(128) k_probe_cost(const float4* __restrict__ pairs, const float4* __restrict__ wtris, uint32_t rootRef,
+                                                    int nRays, float lx, float ly, float lz, float lightLength, uint32_t seedIn,
+                                                    unsigned long long* __restrict__ out)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int inner = 0, tests = 0;
+    if (gid < nRays) {
+        RayRec r;
+        generate_ray(gid, lx, ly, lz, lightLength, seedIn, r);
+        RayCtx ray;
+        ray.dx = r.a.x; ray.dy = r.a.y; ray.dz = r.a.z; ray.ox = r.a.w; ray.oy = r.b.x; ray.oz = r.b.y;
+        ray.dist = kNoHit; ray.tri = 0;
+        ray.noXY = ray.noZZ = ray.rXY = ray.rZZ = ray.ndXY = ray.ndZZ = 0ull;
+        uint32_t stack[64];
+        int sp = 0;
+        uint32_t cur = rootRef;
+        for (;;) {
+            if (cur & kLeafFlag) {
+                uint32_t slot = cur & ~kLeafFlag, w;
+                do {
+                    const float4* t = wtris + 4ull * slot;
+                    F8 ta = ldg256(t), tb = ldg256(t + 2);
+                    w = __float_as_uint(ta.lo.w);
+                    intersect_tri(ray, ta.lo, ta.hi, tb.lo);
+                    tests++;
+                    slot++;
+                } while (!(w & kLastFlag));
+            } else {
+                inner++;
+                const float4* p = pairs + 4ull * cur;
+                W4 ca = ldg256w(p), cb = ldg256w(p + 2);
+                float t1, t2;
+                const bool h1 = intersect_aabb<DIV_IEEE, -1>(ray, ca, t1), h2 = intersect_aabb<DIV_IEEE, -1>(ray, cb, t2);
+                uint32_t first, second;
+                bool pushSecond;
+                if (order_children(h1, h2, t1, t2, child_ref(ca), child_ref(cb), first, second, pushSecond)) {
+                    cur = first;
+                    if (pushSecond) stack[sp++] = second;
+                    continue;
+                }
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        inner += __shfl_down_sync(0xffffffffu, inner, o);
+        tests += __shfl_down_sync(0xffffffffu, tests, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], (unsigned long long)inner);
+        atomicAdd(&out[1], (unsigned long long)tests);
+    }
+}
+
 // ---- per-triangle passes ------------------------------------------------------------------
 // accumulate.cl:4-14
 __global__ void __launch_bounds__(256) k_accumulate(double* __restrict__ photonMap, double* __restrict__ maxPhotonMap,

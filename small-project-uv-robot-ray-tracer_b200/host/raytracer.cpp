@@ -5,6 +5,7 @@
 #include "precomp.h"
 #include "xml_min.h"
 #include "../../include/uvrt.h"
+#include <algorithm>
 #include <cstdio>
 #include <fstream>
 #include <sstream>
@@ -112,9 +113,60 @@ int RayTracer::ShardOwner(long long unit, int U, int N)
 int RayTracer::AutoParts() const
 {
     if (shardParts > 0) return shardParts;
+    if (!shardPlan.empty()) return 1;
     if (shardCount <= 1 || lightPositions.empty()) return 1;
     long long launches = (long long)lightPositions.size() * (maxIterations > 0 ? maxIterations : 1);
     return (launches < 24LL * shardCount && photonsPerLight / 2 >= (1 << 19)) ? 2 : 1;
+}
+
+// Longest-processing-time-first: launches in order of decreasing cost (ties: launch order), each to the rank with the
+// least work so far (ties: lowest rank).  Deterministic, so every rank computes the same plan.
+void RayTracer::PlanShardsLPT(const double* launchCost, int launches, int ranks, int* ownerOut)
+{
+    std::vector<int> order((size_t)launches);
+    for (int k = 0; k < launches; k++) order[(size_t)k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return launchCost[a] > launchCost[b]; });
+    std::vector<double> load((size_t)ranks, 0.0);
+    for (int k : order) {
+        int best = 0;
+        for (int r = 1; r < ranks; r++)
+            if (load[(size_t)r] < load[(size_t)best]) best = r;
+        ownerOut[k] = best;
+        load[(size_t)best] += launchCost[k];
+    }
+}
+
+void RayTracer::PlanShards()
+{
+    shardPlan.clear();
+    if (!ok || shardCount <= 1 || shardParts > 0 || !costAwareSharding || lightPositions.empty() || !mesh) return;
+    const size_t L = lightPositions.size();
+    std::vector<float> key;
+    key.reserve(3 * L + 3);
+    for (const LightPos& lp : lightPositions) { key.push_back(lp.position.x); key.push_back(mesh->floorHeight + lightHeight); key.push_back(lp.position.y); }
+    key.push_back(lightLength);
+    key.push_back((float)mesh->triangleCount);
+    if (key != planKey || positionCost.size() != L) {
+        positionCost.assign(L, 0.0);
+        for (size_t i = 0; i < L; i++) {
+            double inner = 0, tests = 0;
+            // issue-slot weights of one inner-node step and one triangle test of the extend kernel (profiles/r2_fast_extend.md)
+            if (!Check(uvrt_probe_cost(ctx, key[3 * i], key[3 * i + 1], key[3 * i + 2], lightLength, 0u, 8192, &inner, &tests), "probe_cost")) {
+                positionCost.clear();
+                planKey.clear();
+                ok = true;            // a failed probe only costs the plan, not the run
+                return;
+            }
+            positionCost[i] = 44.0 * inner + 75.0 * tests + 50.0;
+        }
+        planKey = key;
+    }
+    const long long launches = (long long)L * (maxIterations > currIterations ? maxIterations - currIterations : 1);
+    if (launches > (1 << 22)) return;
+    std::vector<double> cost((size_t)launches);
+    for (long long k = 0; k < launches; k++) cost[(size_t)k] = positionCost[(size_t)(k % (long long)L)];
+    shardPlan.assign((size_t)launches, 0);
+    PlanShardsLPT(cost.data(), (int)launches, shardCount, shardPlan.data());
 }
 
 // generate.cl:13-39 for work-item 0 (the only one that writes SEED): the seed expression in fp32 from left to
@@ -150,8 +202,10 @@ uint32_t RayTracer::SeedAfterLaunch(float lx, float ly, float lz, float /*lightL
 void RayTracer::BeginWindow()
 {
     const long long L = (long long)lightPositions.size();
-    long long remaining = L;
-    if (launchCounter % L == 0 && maxIterations > currIterations) remaining = (long long)(maxIterations - currIterations) * L;
+    // launches left in the run as planned (launchCounter restarts at ResetDosageMap); a caller that keeps going
+    // beyond maxIterations gets one pass per window
+    long long remaining = (long long)maxIterations * L - launchCounter;
+    if (remaining < 1) remaining = L - launchCounter % L;
     // one int32 row per launch: at most 64 MiB and 256 rows at a time -- a window is one allocation and one all-reduce,
     // and both should have the size they had in the caller's warm-up passes (a 268 MB first-time window cost 1.2 s
     // of allocator and NCCL set-up in the middle of a timed run, profiles/r2_bench_n8_first.json)
@@ -185,10 +239,11 @@ void RayTracer::ComputeSingleLightDosageMap(LightPos lightPos, int photonsPerLig
     } else {
         if (windowRows == 0) BeginWindow();
         if (!ok) return;
-        const int parts = AutoParts();
+        const bool planned = !shardPlan.empty() && launchCounter < (long long)shardPlan.size();
+        const int parts = planned ? 1 : AutoParts();
         const int U = (int)lightPositions.size() * parts;
         for (int j = 0; j < parts; j++) {
-            if (ShardOwner(launchCounter * parts + j, U, shardCount) != shardRank) continue;
+            if ((planned ? shardPlan[(size_t)launchCounter] : ShardOwner(launchCounter * parts + j, U, shardCount)) != shardRank) continue;
             const long long first = (long long)photonsPerLight * j / parts, last = (long long)photonsPerLight * (j + 1) / parts;
             if (last <= first) continue;
             if (!Check(uvrt_trace_row(ctx, windowFill, lightposition.x, lightposition.y, lightposition.z, lightLength, first,
@@ -256,6 +311,7 @@ void RayTracer::ResetDosageMap()
     raysTraced = 0;
     windowRows = windowFill = 0;
     ClearBuffers(true);
+    PlanShards();
 }
 
 void RayTracer::ClearBuffers(bool resetColor)

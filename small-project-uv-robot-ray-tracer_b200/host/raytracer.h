@@ -77,8 +77,14 @@ public:
     // sums over the ranks and folds in launch order: maps bit-identical to the single-GPU run for any split.
     static int ShardOwner(long long unit, int unitsPerPass, int ranks);
     int shardRank = 0, shardCount = 1;
-    int shardParts = 0;          // 0: chosen per run (AutoParts)
+    int shardParts = 0;          // 0: chosen per run (PlanShards / AutoParts)
     int AutoParts() const;
+    // Cost-aware deal (default for shardParts == 0): lamp positions differ in cost by up to 1.4x, so ResetDosageMap
+    // probes every position once per route (uvrt_probe_cost: node visits and triangle tests per ray of a small,
+    // deterministic sample -- identical on every rank) and deals the WHOLE launches of the run longest-first to the
+    // least loaded rank.  Falls back to the rotation of ShardOwner when switched off or when the run outgrows the plan.
+    bool costAwareSharding = true;
+    static void PlanShardsLPT(const double* launchCost, int launches, int ranks, int* ownerOut);
     long long launchCounter = 0;
     long long photonMapSizeTotal = 0;   // photonMapSize without the int overflow (see ComputeSingleLightDosageMap)
     // SEED after a launch at lightposition (generate.cl:13-39 for work-item 0), computed on the host: the chain
@@ -106,6 +112,10 @@ public:
 private:
     bool Check(int rc, const char* what);
     void UploadScene();
+    void PlanShards();
+    std::vector<int> shardPlan;            // owner of launch k of the run being traced; empty: ShardOwner
+    std::vector<float> planKey;            // what positionCost was probed for
+    std::vector<double> positionCost;
     // count-matrix window of a sharded run
     void BeginWindow();
     void FoldWindow();

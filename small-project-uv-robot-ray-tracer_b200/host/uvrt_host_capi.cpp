@@ -301,6 +301,20 @@ int uvrt_sim_set_shard_parts(uvrt_sim* s, int parts)
 
 int uvrt_sim_shard_parts(const uvrt_sim* s) { return s ? s->rt.AutoParts() : 0; }
 
+int uvrt_sim_set_cost_aware(uvrt_sim* s, int on)
+{
+    if (!s) return UVRT_ERR_INVALID;
+    s->rt.costAwareSharding = on != 0;
+    return UVRT_OK;
+}
+
+int uvrt_host_plan_shards(const double* launchCost, int launches, int ranks, int* ownerOut)
+{
+    if (!launchCost || !ownerOut || launches < 0 || ranks < 1) return UVRT_ERR_INVALID;
+    RayTracer::PlanShardsLPT(launchCost, launches, ranks, ownerOut);
+    return UVRT_OK;
+}
+
 int uvrt_sim_set_seed(uvrt_sim* s, uint32_t seed)
 {
     if (!s) return UVRT_ERR_INVALID;

@@ -122,3 +122,26 @@ def test_host_seed_chain_equals_oracle(checkers, room):
             O.orc_generate(None, 0, 0, x, y, z, f32(1.0), seed_in, C.byref(so))
             assert int(H.uvrt_host_seed_after_launch(x, y, z, f32(1.0), seed_in)) == so.value
             seed = int(so.value)
+
+
+def test_cost_aware_plan_is_deterministic_complete_and_balanced():
+    """RayTracer::PlanShardsLPT: every launch gets exactly one owner, the plan depends on nothing but its inputs (so
+    every rank computes the same one), and with the measured position costs of the room the most loaded rank is within
+    one launch-cost-difference of the mean -- against 8.6 % for the rotation at 120 launches on 8 ranks."""
+    import ctypes as C
+    import importlib
+    H = importlib.import_module("small-project-uv-robot-ray-tracer_b200").host()
+    cost12 = np.array([36.2, 32.2, 31.6, 34.2, 33.4, 34.7, 33.3, 38.0, 36.3, 33.9, 35.7, 45.3])
+    for iters, N in ((10, 8), (10, 4), (10, 2), (1, 8), (3, 5), (160, 8)):
+        cost = np.tile(cost12, iters)
+        a, b = np.zeros(len(cost), dtype=np.int32), np.zeros(len(cost), dtype=np.int32)
+        assert H.uvrt_host_plan_shards(T.ptr(cost), len(cost), N, T.ptr(a)) == 0
+        assert H.uvrt_host_plan_shards(T.ptr(cost.copy()), len(cost), N, T.ptr(b)) == 0
+        assert np.array_equal(a, b) and a.min() >= 0 and a.max() < N
+        load = np.bincount(a, weights=cost, minlength=N)
+        assert load.max() - load.min() <= cost12.max() + 1e-9
+        if iters == 10 and N == 8:
+            rot = np.zeros(N)
+            for k in range(len(cost)):
+                rot[H.uvrt_host_shard_owner(k, 12, N)] += cost[k]
+            assert load.max() / load.mean() < 1.01 < 1.08 < rot.max() / rot.mean()

@@ -353,3 +353,126 @@ void lab_fast(const tri_t* tris, ray_t* rays, const ray_t* ref, const node_t* no
     tot.rays = (uint64_t)nRays;
     *out = tot;
 }
+
+/* ---- lockstep warp model: what would postponing leaf tests buy? -----------------------------------
+ * 32 consecutive rays form a warp.  Time advances in rounds; in a round the warp executes the inner-node
+ * step (cost cInner) if any lane wants one and the leaf step (cost cLeaf) if any lane wants one -- two
+ * divergent paths issued one after the other.  policy 0: a lane that reaches a leaf tests it in the next
+ * round (today's kernels).  policy 1: a lane that reaches a leaf parks it (up to `queue` leaves) and keeps
+ * traversing with its stale culling distance; the warp runs a leaf round only when at least `minLanes`
+ * lanes have a parked leaf or nobody can do anything else.  Order is free in the certified scheme, so both are legal.
+ * Returns the summed cost over all warps; out: rounds, inner steps, leaf steps, lane-steps. */
+typedef struct {
+    uint32_t stack[LAB_STACK];
+    uint32_t sp, cur;          /* cur: node index or 0xffffffff */
+    uint32_t pend[4];
+    int npend, done;
+    float best, dcull;
+} lane_t;
+
+static inline int lane_next_node(lane_t* L)
+{
+    if (L->sp == 0) { L->cur = 0xffffffffu; return 0; }
+    L->cur = L->stack[--L->sp];
+    return 1;
+}
+
+double lab_warp_model(const tri_t* tris, const ray_t* rays, const node_t* nodes, const uint32_t* triIdx, int64_t nRays, int policy,
+                      int queue, int minLanes, double cInner, double cLeaf, double cVote, float dRel, float dAbs, uint64_t* out4)
+{
+    double total = 0;
+    uint64_t rounds = 0, innerRounds = 0, leafRounds = 0, innerLaneSteps = 0, leafLaneSteps = 0;
+    const int64_t nGroups = (nRays + 31) / 32;
+    if (queue > 4) queue = 4;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : total, rounds, innerRounds, leafRounds, innerLaneSteps, leafLaneSteps)
+    for (int64_t g = 0; g < nGroups; g++) {
+        lane_t L[32];
+        ray_t R[32];
+        int n = 0;
+        for (int64_t i = g * 32; i < nRays && i < g * 32 + 32; i++, n++) {
+            R[n] = rays[i];
+            L[n].sp = 0; L[n].cur = 0; L[n].npend = 0; L[n].done = 0; L[n].best = 1e30f; L[n].dcull = 3e38f;
+        }
+        for (;;) {
+            int wantInner = 0, wantLeaf = 0, blocked = 0, alive = 0;
+            for (int k = 0; k < n; k++) {
+                lane_t* l = &L[k];
+                if (l->done) continue;
+                alive++;
+                int curIsLeaf = l->cur != 0xffffffffu && nodes[l->cur].triCount > 0;
+                if (policy == 0) {
+                    if (curIsLeaf) wantLeaf++; else if (l->cur != 0xffffffffu) wantInner++;
+                } else {
+                    if (l->cur != 0xffffffffu && !curIsLeaf) wantInner++;
+                    else if (l->npend > 0 || curIsLeaf) { wantLeaf++; if (curIsLeaf || l->cur == 0xffffffffu) blocked++; }
+                }
+            }
+            if (!alive) break;
+            int doLeaf, doInner;
+            if (policy == 0) { doLeaf = wantLeaf > 0; doInner = wantInner > 0; }
+            else {
+                int pendLanes = 0;
+                for (int k = 0; k < n; k++) if (!L[k].done && (L[k].npend > 0 || (L[k].cur != 0xffffffffu && nodes[L[k].cur].triCount > 0))) pendLanes++;
+                doLeaf = pendLanes >= minLanes || wantInner == 0;
+                doInner = !doLeaf && wantInner > 0;
+                total += cVote;
+            }
+            rounds++;
+            if (doInner) {
+                innerRounds++;
+                total += cInner;
+                for (int k = 0; k < n; k++) {
+                    lane_t* l = &L[k];
+                    if (l->done || l->cur == 0xffffffffu || nodes[l->cur].triCount > 0) continue;
+                    innerLaneSteps++;
+                    const node_t* nd = &nodes[l->cur];
+                    uint32_t k1 = (uint32_t)nd->leftFirst, k2 = k1 + 1;
+                    float t1, t2;
+                    int h1 = box_exact(&R[k], &nodes[k1], &t1) && t1 < l->dcull, h2 = box_exact(&R[k], &nodes[k2], &t2) && t2 < l->dcull;
+                    if (h2 && (!h1 || t1 > t2)) { uint32_t t = k1; k1 = k2; k2 = t; int h = h1; h1 = h2; h2 = h; }
+                    if (h1) { l->cur = k1; if (h2) l->stack[l->sp++] = k2; }
+                    else lane_next_node(l);
+                    if (policy == 1) {
+                        /* park leaves while there is room and something else to do */
+                        while (l->cur != 0xffffffffu && nodes[l->cur].triCount > 0 && l->npend < queue) {
+                            l->pend[l->npend++] = l->cur;
+                            lane_next_node(l);
+                        }
+                    }
+                }
+            }
+            if (doLeaf) {
+                leafRounds++;
+                total += cLeaf;
+                for (int k = 0; k < n; k++) {
+                    lane_t* l = &L[k];
+                    if (l->done) continue;
+                    uint32_t leaf = 0xffffffffu;
+                    if (policy == 0) {
+                        if (l->cur != 0xffffffffu && nodes[l->cur].triCount > 0) { leaf = l->cur; lane_next_node(l); }
+                    } else {
+                        if (l->npend > 0) { leaf = l->pend[0]; for (int q = 1; q < l->npend; q++) l->pend[q - 1] = l->pend[q]; l->npend--; }
+                        else if (l->cur != 0xffffffffu && nodes[l->cur].triCount > 0) { leaf = l->cur; lane_next_node(l); }
+                    }
+                    if (leaf == 0xffffffffu) continue;
+                    leafLaneSteps++;
+                    const node_t* nd = &nodes[leaf];
+                    for (uint32_t i = 0; i < (uint32_t)nd->triCount; i++) {
+                        float t;
+                        if (tri_accept(&R[k], &tris[triIdx[nd->leftFirst + i]], &t) && t < l->best) {
+                            l->best = t;
+                            l->dcull = t * (1.0f + 2.0f * dRel) + 2.0f * dAbs;
+                        }
+                    }
+                }
+            }
+            for (int k = 0; k < n; k++) {
+                lane_t* l = &L[k];
+                if (!l->done && l->cur == 0xffffffffu && l->sp == 0 && l->npend == 0) l->done = 1;
+                else if (!l->done && l->cur == 0xffffffffu && l->sp > 0) lane_next_node(l);
+            }
+        }
+    }
+    out4[0] = rounds; out4[1] = innerRounds; out4[2] = leafRounds; out4[3] = innerLaneSteps; out4[4] = leafLaneSteps;
+    return total;
+}
