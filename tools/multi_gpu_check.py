@@ -3,8 +3,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \\
         --master-port 29533 tools/multi_gpu_check.py
 
-1. The default run of BASELINE configs[1] (route.xml, 10 iterations, 335,544,240 rays) shared between the ranks, with
-   whole launches (parts 1) and with launches cut into ray ranges (parts 2 and 4): photon map, max map, dose and
+1. The default run of BASELINE configs[1] (route.xml, 10 iterations, 335,544,240 rays) shared between the ranks -- the
+   cost-aware plan of whole launches (default), the rotation with its automatic choice of ranges, whole launches
+   (parts 1) and launches cut into ray ranges (parts 2 and 4): photon map, max map, dose and
    colours must hash to the golden the reference's own compiled sources produced (tests/golden/route_runs.json).
 2. A smaller run with awkward durations: the sharded result must equal, bit for bit, what rank 0 gets alone.
 Every rank traces its units (RayTracer::ShardOwner), the integer count rows are summed by ONE ncclAllReduce per
@@ -47,8 +48,9 @@ def main():
     sim.set_shard(rank, world)
     golden = json.load(open(os.path.join(ROOT, "tests", "golden", "route_runs.json")))["runs"]["route"]["after_iteration"][9]
     ok = True
-    for parts in (0, 1, 2, 4):
-        sim.set_shard_parts(parts)
+    for parts in (0, -1, 1, 2, 4):         # 0: cost-aware plan of whole launches (default); -1: rotation + AutoParts; else fixed ranges
+        sim.set_cost_aware(parts == 0)
+        sim.set_shard_parts(max(parts, 0))
         sim.set_seed(0)
         dose = sim.run()                      # ResetDosageMap, all passes, Reduce (all-reduce + fold), Shade, read-back
         got = (fnv(ctx.read(uv.BUF.SUM)), fnv(ctx.read(uv.BUF.MAX)), fnv(dose), fnv(ctx.read(uv.BUF.COLOR)), int(sim.params.seedState))

@@ -55,6 +55,7 @@ def summarise(path, wall_ms):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--parts", type=int, default=0)
+    ap.add_argument("--cost-aware", type=int, default=1)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline"))
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
@@ -77,6 +78,7 @@ def main():
         ctx.comm_init(bytes(idt.cpu().tolist()), rank, world)
         sim.set_shard(rank, world)
         sim.set_shard_parts(args.parts)
+        sim.set_cost_aware(bool(args.cost_aware))
     for _ in range(2):
         sim.run()
     best = None
@@ -97,7 +99,7 @@ def main():
             ctx.timeline_dump(path)
         ctx.set_option("timeline", 0)
     s = summarise(f"{args.out}_n{world}_rank{rank}.json", best)
-    s.update({"n_gpus": world, "rank": rank, "parts": sim.shard_parts()})
+    s.update({"n_gpus": world, "rank": rank, "parts": sim.shard_parts(), "cost_aware": int(bool(args.cost_aware) and args.parts == 0)})
     if dist is not None:
         import torch
         gathered = [None] * world
