@@ -166,7 +166,10 @@ void RayTracer::PlanShards()
     std::vector<double> cost((size_t)launches);
     for (long long k = 0; k < launches; k++) cost[(size_t)k] = positionCost[(size_t)(k % (long long)L)];
     shardPlan.assign((size_t)launches, 0);
-    PlanShardsLPT(cost.data(), (int)launches, shardCount, shardPlan.data());
+    // every window of the count matrix ends in an all-reduce, i.e. the ranks meet there: balance each window on its own
+    const long long W = MaxWindowRows();
+    for (long long k0 = 0; k0 < launches; k0 += W)
+        PlanShardsLPT(cost.data() + k0, (int)std::min(W, launches - k0), shardCount, shardPlan.data() + k0);
 }
 
 // generate.cl:13-39 for work-item 0 (the only one that writes SEED): the seed expression in fp32 from left to
@@ -199,6 +202,17 @@ uint32_t RayTracer::SeedAfterLaunch(float lx, float ly, float lz, float /*lightL
     return s;
 }
 
+// One int32 row per launch: at most 64 MiB and 256 rows at a time -- a window is one allocation and one all-reduce,
+// and both should have the size they had in the caller's warm-up passes (a 268 MB first-time window cost 1.2 s of
+// allocator and NCCL set-up in the middle of a timed run, profiles/r2_bench_n8_first.json).
+long long RayTracer::MaxWindowRows() const
+{
+    long long maxRows = (64LL << 20) / (4LL * (mesh && mesh->triangleCount > 0 ? mesh->triangleCount : 1));
+    if (maxRows < 1) maxRows = 1;
+    if (maxRows > 256) maxRows = 256;
+    return maxRows;
+}
+
 void RayTracer::BeginWindow()
 {
     const long long L = (long long)lightPositions.size();
@@ -206,12 +220,7 @@ void RayTracer::BeginWindow()
     // beyond maxIterations gets one pass per window
     long long remaining = (long long)maxIterations * L - launchCounter;
     if (remaining < 1) remaining = L - launchCounter % L;
-    // one int32 row per launch: at most 64 MiB and 256 rows at a time -- a window is one allocation and one all-reduce,
-    // and both should have the size they had in the caller's warm-up passes (a 268 MB first-time window cost 1.2 s
-    // of allocator and NCCL set-up in the middle of a timed run, profiles/r2_bench_n8_first.json)
-    long long maxRows = (64LL << 20) / (4LL * (mesh->triangleCount > 0 ? mesh->triangleCount : 1));
-    if (maxRows < 1) maxRows = 1;
-    if (maxRows > 256) maxRows = 256;
+    const long long maxRows = MaxWindowRows();
     windowRows = (int)(remaining < maxRows ? remaining : maxRows);
     windowFill = 0;
     windowDurations.assign((size_t)windowRows, 0.0f);

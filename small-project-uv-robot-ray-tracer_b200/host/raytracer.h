@@ -113,6 +113,7 @@ private:
     bool Check(int rc, const char* what);
     void UploadScene();
     void PlanShards();
+    long long MaxWindowRows() const;
     std::vector<int> shardPlan;            // owner of launch k of the run being traced; empty: ShardOwner
     std::vector<float> planKey;            // what positionCost was probed for
     std::vector<double> positionCost;
