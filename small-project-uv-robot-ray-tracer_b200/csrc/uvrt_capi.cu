@@ -195,11 +195,17 @@ struct uvrt_ctx {
     int refill = 24;          // persistent kernels: refill when fewer lanes than this are busy
 
     // count matrix (uvrt_matrix_*): one int32 row of nTris counters per launch of a run / window
-    int* dMatrix = nullptr;
-    size_t matrixCap = 0;                // capacity in int32 elements
+    // Two buffers alternate from window to window, so that the all-reduce + fold of window k (main stream) run next
+    // to the extends of window k+1 (extend streams) instead of draining the pipeline at every window boundary.
+    int* dMatrix = nullptr;              // the current window's buffer (= matrixBuf[matrixSel])
+    int* matrixBuf[2] = {nullptr, nullptr};
+    size_t matrixCap[2] = {0, 0};        // capacities in int32 elements
+    int matrixSel = 1;
     int matrixRows = 0;
-    float* dDurations = nullptr;
-    int durCap = 0;
+    float* durBuf[2] = {nullptr, nullptr};
+    int durCap[2] = {0, 0};
+    cudaEvent_t matrixReady[2] = {nullptr, nullptr}, matrixFolded[2] = {nullptr, nullptr};
+    bool matrixFoldedUsed[2] = {false, false};
 
     // measurement
     int timeline = 0;                    // option "timeline": host-side call log + device times of every stage launch
@@ -725,8 +731,12 @@ void uvrt_destroy(uvrt_ctx* ctx)
     if (ctx->dQPairs) cudaFree(ctx->dQPairs);
     if (ctx->dFastGrid) cudaFree(ctx->dFastGrid);
     if (ctx->dFastStats) cudaFree(ctx->dFastStats);
-    if (ctx->dMatrix) cudaFree(ctx->dMatrix);
-    if (ctx->dDurations) cudaFree(ctx->dDurations);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->matrixBuf[k]) cudaFree(ctx->matrixBuf[k]);
+        if (ctx->durBuf[k]) cudaFree(ctx->durBuf[k]);
+        if (ctx->matrixReady[k]) cudaEventDestroy(ctx->matrixReady[k]);
+        if (ctx->matrixFolded[k]) cudaEventDestroy(ctx->matrixFolded[k]);
+    }
     if (ctx->timelineOrigin) cudaEventDestroy(ctx->timelineOrigin);
     if (ctx->dVertsSpare) cudaFree(ctx->dVertsSpare);
     if (ctx->vertsEv) cudaEventDestroy(ctx->vertsEv);
@@ -1629,26 +1639,54 @@ int uvrt_probe_cost(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLeng
 // then bit-identical to the single-GPU run for ANY split and ANY durations.
 int uvrt_matrix_begin(uvrt_ctx* ctx, int rows)
 {
-    NEED_SCENE();
+    if (!ctx) return UVRT_ERR_INVALID;
+    if (!ctx->nTris) return fail(ctx, UVRT_ERR_NO_SCENE, "%s: no scene uploaded", __func__);
+    const bool foreign = ctx->mainForeign;
+    ApiScope api_(ctx, "uvrt_matrix_begin");
+    Bind bind_(ctx);
     if (rows < 1) return fail(ctx, UVRT_ERR_INVALID, "matrix_begin: rows = %d", rows);
     const size_t need = (size_t)rows * (size_t)ctx->nTris;
-    if (need > ctx->matrixCap) {
+    const int sel = ctx->matrixSel ^ 1;
+    for (int k = 0; k < 2; k++) {
+        if (!ctx->matrixReady[k]) CK(cudaEventCreateWithFlags(&ctx->matrixReady[k], cudaEventDisableTiming));
+        if (!ctx->matrixFolded[k]) CK(cudaEventCreateWithFlags(&ctx->matrixFolded[k], cudaEventDisableTiming));
+    }
+    if (need > ctx->matrixCap[sel]) {
         int* fresh = nullptr;
         CK(cudaMalloc((void**)&fresh, need * 4));
-        if (ctx->dMatrix) cudaFree(ctx->dMatrix);
-        ctx->dMatrix = fresh;
-        ctx->matrixCap = need;
+        if (ctx->matrixBuf[sel]) cudaFree(ctx->matrixBuf[sel]);     // (synchronises the device: nothing reads it any more)
+        ctx->matrixBuf[sel] = fresh;
+        ctx->matrixCap[sel] = need;
+        ctx->matrixFoldedUsed[sel] = false;
     }
-    if (rows > ctx->durCap) {
+    if (rows > ctx->durCap[sel]) {
         float* fresh = nullptr;
         CK(cudaMalloc((void**)&fresh, (size_t)rows * 4));
-        if (ctx->dDurations) cudaFree(ctx->dDurations);
-        ctx->dDurations = fresh;
-        ctx->durCap = rows;
+        if (ctx->durBuf[sel]) cudaFree(ctx->durBuf[sel]);
+        ctx->durBuf[sel] = fresh;
+        ctx->durCap[sel] = rows;
     }
-    // the rows of the previous window may still be read by its fold on the main stream: same stream, in order
-    CK(cudaMemsetAsync(ctx->dMatrix, 0, need * 4, ctx->stream));
+    // Zeroed on the (otherwise idle) accumulate stream: after the fold that last read this buffer (two windows ago) and,
+    // when something other than matrix calls happened on the main stream since the last trace (reset, upload), after
+    // that; the extend streams wait for the zeroing only -- not for the main stream, where the previous window's
+    // all-reduce and fold may still be running.
+    if (foreign) {
+        CK(cudaEventRecord(ctx->forkEv, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->accStream, ctx->forkEv, 0));
+    }
+    if (ctx->matrixFoldedUsed[sel]) CK(cudaStreamWaitEvent(ctx->accStream, ctx->matrixFolded[sel], 0));
+    // rows of this buffer may still be written by extends of the window before the previous one only if the caller never
+    // folded it; waiting for the extend streams' last events covers that case too
+    for (int k = 0; k < 2; k++)
+        if (ctx->extUsed[k] && !ctx->matrixFoldedUsed[sel]) CK(cudaStreamWaitEvent(ctx->accStream, ctx->extDone[k], 0));
+    CK(cudaMemsetAsync(ctx->matrixBuf[sel], 0, need * 4, ctx->accStream));
+    CK(cudaEventRecord(ctx->matrixReady[sel], ctx->accStream));
+    CK(cudaStreamWaitEvent(ctx->extStream[0], ctx->matrixReady[sel], 0));
+    CK(cudaStreamWaitEvent(ctx->extStream[1], ctx->matrixReady[sel], 0));
+    ctx->matrixSel = sel;
+    ctx->dMatrix = ctx->matrixBuf[sel];
     ctx->matrixRows = rows;
+    ctx->mainForeign = foreign;          // a matrix call is not a reason for the next trace to wait for the main stream
     return UVRT_OK;
 }
 
@@ -1707,12 +1745,19 @@ int uvrt_trace_row(uvrt_ctx* ctx, int row, float lx, float ly, float lz, float l
 
 int uvrt_matrix_fold(uvrt_ctx* ctx, const float* durations, int rows, int reduce)
 {
-    NEED_SCENE();
+    if (!ctx) return UVRT_ERR_INVALID;
+    if (!ctx->nTris) return fail(ctx, UVRT_ERR_NO_SCENE, "%s: no scene uploaded", __func__);
+    const bool foreign = ctx->mainForeign;
+    ApiScope api_(ctx, "uvrt_matrix_fold");
+    Bind bind_(ctx);
     if (rows < 0 || rows > ctx->matrixRows || (rows > 0 && !durations))
         return fail(ctx, UVRT_ERR_INVALID, "matrix_fold: rows = %d of %d", rows, ctx->matrixRows);
+    const int sel = ctx->matrixSel;
+    // the extends of this window are the last work on the extend streams (the next window's are not enqueued yet)
     for (int k = 0; k < 2; k++)
         if (ctx->extUsed[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->extDone[k], 0));
-    if (rows == 0) return UVRT_OK;
+    if (ctx->matrixReady[sel]) CK(cudaStreamWaitEvent(ctx->stream, ctx->matrixReady[sel], 0));
+    if (rows == 0) { ctx->mainForeign = foreign; return UVRT_OK; }
     if (reduce && (ctx->nRanks > 1 || ctx->comm)) {
         if (!ctx->comm) return fail(ctx, UVRT_ERR_NCCL, "matrix_fold: uvrt_comm_init was not called");
         nvtxRangePushA("ncclAllReduce(count matrix)");
@@ -1720,13 +1765,17 @@ int uvrt_matrix_fold(uvrt_ctx* ctx, const float* durations, int rows, int reduce
         nvtxRangePop();
         if (r != kNcclSuccess) return fail(ctx, UVRT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
     }
-    CK(cudaMemcpyAsync(ctx->dDurations, durations, (size_t)rows * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // (pageable source: staged before the call returns, so the caller may reuse `durations` at once)
+    CK(cudaMemcpyAsync(ctx->durBuf[sel], durations, (size_t)rows * 4, cudaMemcpyHostToDevice, ctx->stream));
     {
         StageTimer t(ctx, UVRT_STAGE_ACCUMULATE);
-        k_fold_rows<<<grid_for(ctx->nTris, 256), 256, 0, ctx->stream>>>(ctx->dSum, ctx->dMax, ctx->dMatrix, ctx->dDurations, rows, ctx->nTris);
+        k_fold_rows<<<grid_for(ctx->nTris, 256), 256, 0, ctx->stream>>>(ctx->dSum, ctx->dMax, ctx->dMatrix, ctx->durBuf[sel], rows, ctx->nTris);
     }
     ctx->launches++;
     CK_LAUNCH("fold");
+    CK(cudaEventRecord(ctx->matrixFolded[sel], ctx->stream));
+    ctx->matrixFoldedUsed[sel] = true;
+    ctx->mainForeign = foreign;
     return UVRT_OK;
 }
 
@@ -1817,9 +1866,11 @@ int uvrt_read(uvrt_ctx* ctx, uvrt_buffer what, void* dst, size_t bytes)
     int rc = check_buffer(ctx, what, &p, &cap);
     if (rc) return rc;
     if (!dst || bytes > cap) return fail(ctx, UVRT_ERR_INVALID, "read: %zu bytes requested, buffer %d holds %zu", bytes, (int)what, cap);
-    if (what == UVRT_BUF_MATRIX)      // rows are written by the extend streams of uvrt_trace_row
+    if (what == UVRT_BUF_MATRIX) {    // rows are zeroed on the accumulate stream and written by the extend streams of uvrt_trace_row
+        if (ctx->matrixReady[ctx->matrixSel]) CK(cudaStreamWaitEvent(ctx->stream, ctx->matrixReady[ctx->matrixSel], 0));
         for (int k = 0; k < 2; k++)
             if (ctx->extUsed[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->extDone[k], 0));
+    }
     if (bytes) CK(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return UVRT_OK;
@@ -1845,9 +1896,11 @@ int uvrt_write(uvrt_ctx* ctx, uvrt_buffer what, const void* src, size_t bytes)
     int rc = check_buffer(ctx, what, &p, &cap);
     if (rc) return rc;
     if (!src || bytes > cap) return fail(ctx, UVRT_ERR_INVALID, "write: %zu bytes offered, buffer %d holds %zu", bytes, (int)what, cap);
-    if (what == UVRT_BUF_MATRIX)
+    if (what == UVRT_BUF_MATRIX) {
+        if (ctx->matrixReady[ctx->matrixSel]) CK(cudaStreamWaitEvent(ctx->stream, ctx->matrixReady[ctx->matrixSel], 0));
         for (int k = 0; k < 2; k++)
             if (ctx->extUsed[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->extDone[k], 0));
+    }
     if (bytes) CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (what == UVRT_BUF_COUNTS) ctx->countsDirty = true;
