@@ -1977,7 +1977,19 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
 {
     if (!ctx || !key) return UVRT_ERR_INVALID;
     if (!strcmp(key, "extend_variant")) ctx->extendVariant = value;
-    else if (!strcmp(key, "stage_timing")) ctx->stageTiming = value;
+    else if (!strcmp(key, "stage_timing")) {
+        ctx->stageTiming = value;
+        if (value && ctx->freeEvents.size() < 8192) {
+            // two events per stage launch: create them now, not inside the region being timed (cudaEventCreate costs
+            // microseconds, more when eight processes share the driver: 16 ms of a 126 ms timed run at 8 GPUs)
+            Bind b(ctx);
+            while (ctx->freeEvents.size() < 8192) {
+                cudaEvent_t e = nullptr;
+                if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); break; }
+                ctx->freeEvents.push_back(e);
+            }
+        }
+    }
     else if (!strcmp(key, "timeline")) {
         Bind b(ctx);
         uvrt_stage_time_reset(ctx);
