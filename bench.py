@@ -91,6 +91,9 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.rows, self.proc = [], None
+        self.windows = {}
+        if gpu_index < 0:
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
@@ -99,7 +102,6 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
-        self.windows = {}
 
     def _read(self):
         for line in self.proc.stdout:
@@ -364,11 +366,13 @@ def main():
                 break
         return total_ms, done
 
+    # the clock sampler (nvidia-smi -lms) starts BEFORE the warm-up: its start-up (NVML initialisation over every GPU of
+    # the box) perturbs the devices for tens of milliseconds, which is a fifth of the 20-step timed region; rank 0's GPU only
+    clocks = ClockSampler(local if rank == 0 else -1)
     run_steps(max(args.warmup, 3))
     ctx.set_option("stage_timing", 1)
     ctx.stage_time_reset()
     launches0 = ctx.launch_count()
-    clocks = ClockSampler(local)
     barrier()
     clocks.begin("timed")
     ms, _ = run_steps(args.steps)

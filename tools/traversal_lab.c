@@ -476,3 +476,95 @@ double lab_warp_model(const tri_t* tris, const ray_t* rays, const node_t* nodes,
     out4[0] = rounds; out4[1] = innerRounds; out4[2] = leafRounds; out4[3] = innerLaneSteps; out4[4] = leafLaneSteps;
     return total;
 }
+
+
+/* policy with refill: a warp owns `chunk` consecutive rays and puts the next one into a lane as soon as the lane's ray is
+ * done (at a round boundary); leaves are parked as in policy 1 of lab_warp_model.  Same cost model. */
+double lab_warp_model_refill(const tri_t* tris, const ray_t* rays, const node_t* nodes, const uint32_t* triIdx, int64_t nRays, int chunk,
+                             int queue, int minLanes, double cInner, double cLeaf, double cVote, float dRel, float dAbs, uint64_t* out5)
+{
+    double total = 0;
+    uint64_t rounds = 0, innerRounds = 0, leafRounds = 0, innerLaneSteps = 0, leafLaneSteps = 0;
+    const int64_t nGroups = (nRays + chunk - 1) / chunk;
+    if (queue > 4) queue = 4;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : total, rounds, innerRounds, leafRounds, innerLaneSteps, leafLaneSteps)
+    for (int64_t g = 0; g < nGroups; g++) {
+        lane_t L[32];
+        ray_t R[32];
+        int64_t next = g * chunk;
+        const int64_t end = (g + 1) * chunk < nRays ? (g + 1) * chunk : nRays;
+        for (int k = 0; k < 32; k++) L[k].done = 1;
+        for (;;) {
+            /* refill */
+            int alive = 0;
+            for (int k = 0; k < 32; k++) {
+                if (L[k].done && next < end) {
+                    R[k] = rays[next++];
+                    L[k].sp = 0; L[k].cur = 0; L[k].npend = 0; L[k].done = 0; L[k].best = 1e30f; L[k].dcull = 3e38f;
+                }
+                if (!L[k].done) alive++;
+            }
+            if (!alive) break;
+            int wantInner = 0, pendLanes = 0;
+            for (int k = 0; k < 32; k++) {
+                lane_t* l = &L[k];
+                if (l->done) continue;
+                int curIsLeaf = l->cur != 0xffffffffu && nodes[l->cur].triCount > 0;
+                if (l->cur != 0xffffffffu && !curIsLeaf) wantInner++;
+                if (l->npend > 0 || curIsLeaf) pendLanes++;
+            }
+            const int doLeaf = pendLanes >= minLanes || wantInner == 0;
+            const int doInner = !doLeaf && wantInner > 0;
+            total += cVote;
+            rounds++;
+            if (doInner) {
+                innerRounds++;
+                total += cInner;
+                for (int k = 0; k < 32; k++) {
+                    lane_t* l = &L[k];
+                    if (l->done || l->cur == 0xffffffffu || nodes[l->cur].triCount > 0) continue;
+                    innerLaneSteps++;
+                    const node_t* nd = &nodes[l->cur];
+                    uint32_t k1 = (uint32_t)nd->leftFirst, k2 = k1 + 1;
+                    float t1, t2;
+                    int h1 = box_exact(&R[k], &nodes[k1], &t1) && t1 < l->dcull, h2 = box_exact(&R[k], &nodes[k2], &t2) && t2 < l->dcull;
+                    if (h2 && (!h1 || t1 > t2)) { uint32_t t = k1; k1 = k2; k2 = t; int h = h1; h1 = h2; h2 = h; }
+                    if (h1) { l->cur = k1; if (h2) l->stack[l->sp++] = k2; }
+                    else lane_next_node(l);
+                    while (l->cur != 0xffffffffu && nodes[l->cur].triCount > 0 && l->npend < queue) {
+                        l->pend[l->npend++] = l->cur;
+                        lane_next_node(l);
+                    }
+                }
+            }
+            if (doLeaf) {
+                leafRounds++;
+                total += cLeaf;
+                for (int k = 0; k < 32; k++) {
+                    lane_t* l = &L[k];
+                    if (l->done) continue;
+                    uint32_t leaf = 0xffffffffu;
+                    if (l->npend > 0) { leaf = l->pend[0]; for (int q = 1; q < l->npend; q++) l->pend[q - 1] = l->pend[q]; l->npend--; }
+                    else if (l->cur != 0xffffffffu && nodes[l->cur].triCount > 0) { leaf = l->cur; lane_next_node(l); }
+                    if (leaf == 0xffffffffu) continue;
+                    leafLaneSteps++;
+                    const node_t* nd = &nodes[leaf];
+                    for (uint32_t i = 0; i < (uint32_t)nd->triCount; i++) {
+                        float t;
+                        if (tri_accept(&R[k], &tris[triIdx[nd->leftFirst + i]], &t) && t < l->best) {
+                            l->best = t;
+                            l->dcull = t * (1.0f + 2.0f * dRel) + 2.0f * dAbs;
+                        }
+                    }
+                }
+            }
+            for (int k = 0; k < 32; k++) {
+                lane_t* l = &L[k];
+                if (!l->done && l->cur == 0xffffffffu && l->sp == 0 && l->npend == 0) l->done = 1;
+                else if (!l->done && l->cur == 0xffffffffu && l->sp > 0) lane_next_node(l);
+            }
+        }
+    }
+    out5[0] = rounds; out5[1] = innerRounds; out5[2] = leafRounds; out5[3] = innerLaneSteps; out5[4] = leafLaneSteps;
+    return total;
+}
