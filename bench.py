@@ -418,7 +418,8 @@ def main():
         sim.shade()
         return sim.read_dose()                           # device -> host (synchronises)
 
-    e2e_step()
+    for _ in range(3):
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

@@ -595,10 +595,8 @@ int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
     k_extend_fast<kStack, THREADS, MINB><<<grid_for(nRays, THREADS), THREADS, 0, ctx->xStream>>>(                          \
         ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->dQPairs, ctx->dFastGrid, (uint32_t)nRays, perm, ctx->dFastStats, ctx->fastCheck)
             // "fast_cfg": 0 = 128 threads, at most 48 registers (47 used; 40 resident warps per SM; the default),
-            // 1 = at most 64 registers (54 used; 32 warps), 2 = 256-thread blocks, 3 = 64-thread blocks (both 48 registers)
+            // 1 = at most 64 registers (54 used; 32 warps).  (64-thread blocks: the same; 256-thread blocks: 2.5 % slower.)
             if (ctx->fastCfg == 1) UVRT_FAST_LAUNCH(128, 8);
-            else if (ctx->fastCfg == 2) UVRT_FAST_LAUNCH(256, 5);
-            else if (ctx->fastCfg == 3) UVRT_FAST_LAUNCH(64, 20);
             else UVRT_FAST_LAUNCH(128, 10);
 #undef UVRT_FAST_LAUNCH
         } else

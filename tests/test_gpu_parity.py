@@ -280,9 +280,11 @@ def test_full_pass_matches_golden(uv, room, golden):
     sim.close()
 
 
-def test_sharded_run_equals_single(uv, room):
-    """Launches dealt round-robin to two 'ranks' (here: two contexts on one GPU, combined on the
-    host the way uvrt_reduce combines them) reproduce the single-context maps exactly."""
+@pytest.mark.parametrize("deal", ["rotation", "cost_aware"])
+def test_sharded_run_equals_single(uv, room, deal):
+    """Whole launches shared between two 'ranks' (here: two contexts on one GPU whose maps are combined on the host) --
+    by the rotation of RayTracer::ShardOwner, or by the cost-aware plan (every rank probes the lamp positions on its own
+    and must arrive at the same deal) -- reproduce the single-context maps exactly."""
     results = []
     for rank, count in ((0, 1), (0, 2), (1, 2)):
         sim = uv.Sim(asset_root=T.DATA)
@@ -290,7 +292,8 @@ def test_sharded_run_equals_single(uv, room):
         sim.init("route")
         sim.set_params(photonCount=1 << 21, maxIterations=3)
         sim.set_shard(rank, count)
-        sim.set_shard_parts(1)                   # whole launches: per-rank maxima can be combined with max()
+        sim.set_shard_parts(1 if deal == "rotation" else 0)   # whole launches either way: per-rank maxima combine with max()
+        sim.set_cost_aware(deal == "cost_aware")
         sim.reset_dosage_map()
         while not sim.tick():
             pass
@@ -1004,3 +1007,30 @@ def test_fast_extend_falls_back_on_scenes_it_cannot_serve(uv, room):
         out.append((c.read(uv.BUF.RAYS, 200_000).tobytes(), c.read(uv.BUF.COUNTS).tobytes()))
     assert out[0] == out[1]
     c.close()
+
+
+def test_cost_probe_is_deterministic_and_tracks_the_oracle_counters(uv, ctx, room):
+    """uvrt_probe_cost (the measurement behind the cost-aware deal): the same numbers on every context, equal to the
+    oracle's traversal counters on the same rays, and different enough between lamp positions to matter."""
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_route("route")
+    pos, p = sim.positions, sim.params
+    sim.close()
+    f32 = np.float32
+    tris, nodes, tri_idx, floor = room
+    other = uv.Context(0)
+    other.upload_scene(tris, nodes, tri_idx)
+    costs = []
+    for k in (0, 5, 11):
+        lp = (f32(pos[k, 0]), f32(f32(floor) + f32(p.lightHeight)), f32(pos[k, 1]))
+        a = ctx.probe_cost(lp, p.lightLength, 0, 8192)
+        assert a == other.probe_cost(lp, p.lightLength, 0, 8192)
+        rays = np.zeros(8192, dtype=T.RAY_DT)
+        T.oracle().orc_generate(T.ptr(rays), 0, 8192, lp[0], lp[1], lp[2], f32(p.lightLength), 0, None)
+        cnt = T.Counters()
+        temp = np.zeros(tris.shape[0], dtype=np.int32)
+        T.oracle().orc_extend(T.ptr(temp), T.ptr(tris), T.ptr(rays), T.ptr(nodes), T.ptr(tri_idx), 8192, 0, C.byref(cnt))
+        assert a == (cnt.innerVisits / 8192, cnt.triTests / 8192)
+        costs.append(44 * a[0] + 75 * a[1])
+    other.close()
+    assert max(costs) / min(costs) > 1.1

@@ -56,7 +56,7 @@ def main():
         lp = lamps[pi]
         ref = None
         for v in [int(x) for x in args.variants.split(",")]:
-            for cfg in ((0, 1, 2, 3) if v >= 50 else (0,)):
+            for cfg in ((0, 1) if v >= 50 else (0,)):
                 c.set_option("extend_variant", v)
                 c.set_option("fast_cfg", cfg)
                 c.set_option("fast_check", 0)
