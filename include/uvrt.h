@@ -162,11 +162,13 @@ int uvrt_probe_cost(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLeng
  * (its share of the rays) into row k of a rows x nTris int32 matrix, the rows are summed over the ranks with
  * ONE ncclAllReduce, and the fold replays accumulate row by row in launch order on every rank: photon map and
  * max map are then bit-identical to the single-GPU run for any split and any durations.
- *   uvrt_matrix_begin  sizes and zeroes the matrix (a run, or a window of a long run)
+ *   uvrt_matrix_begin  sizes and zeroes the matrix (a run, or a window of a long run); two buffers alternate from window
+ *                      to window, so the all-reduce + fold of one window run next to the extends of the next
  *   uvrt_trace_row     generate -> (bin) -> extend of rays [firstRay, firstRay + nRays) of a launch, counted in
  *                      `row`; asynchronous, consecutive calls overlap like uvrt_trace
  *   uvrt_matrix_fold   (reduce != 0 and a communicator exists: all-reduce of the first `rows` rows, then)
  *                      UVRT_BUF_SUM += count x durations[r], UVRT_BUF_MAX = max(., count) for r = 0 .. rows-1 */
+int uvrt_matrix_reserve(uvrt_ctx* ctx, int rows);   /* optional: capacity for windows of up to `rows` rows, allocated now */
 int uvrt_matrix_begin(uvrt_ctx* ctx, int rows);
 int uvrt_trace_row(uvrt_ctx* ctx, int row, float lx, float ly, float lz, float lightLength,
                    int64_t firstRay, int64_t nRays, uint32_t seedIn);

@@ -104,6 +104,7 @@ def lib():
         "uvrt_reduce": (i, [vp]),
         "uvrt_reduce_counts": (i, [vp]),
         "uvrt_probe_cost": (i, [vp, f, f, f, f, u32, i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "uvrt_matrix_reserve": (i, [vp, i]),
         "uvrt_matrix_begin": (i, [vp, i]),
         "uvrt_trace_row": (i, [vp, i, f, f, f, f, i64, i64, u32]),
         "uvrt_matrix_fold": (i, [vp, vp, i, i]),

@@ -1638,6 +1638,34 @@ int uvrt_probe_cost(uvrt_ctx* ctx, float lx, float ly, float lz, float lightLeng
 // traces its rays of launch k into row k, ONE all-reduce sums the integer rows, and the fold replays
 // accumulate.cl:4-14 row by row in launch order on every rank -- the f64 sums and the per-launch maxima are
 // then bit-identical to the single-GPU run for ANY split and ANY durations.
+// Capacity for windows of up to `rows` rows in both buffers, so that no later uvrt_matrix_begin has to allocate
+// (an allocation synchronises the device -- the wrong thing to happen inside somebody's timed run).
+int uvrt_matrix_reserve(uvrt_ctx* ctx, int rows)
+{
+    NEED_SCENE();
+    if (rows < 1) return fail(ctx, UVRT_ERR_INVALID, "matrix_reserve: rows = %d", rows);
+    const size_t need = (size_t)rows * (size_t)ctx->nTris;
+    for (int sel = 0; sel < 2; sel++) {
+        if (need > ctx->matrixCap[sel]) {
+            int* fresh = nullptr;
+            CK(cudaMalloc((void**)&fresh, need * 4));
+            if (ctx->matrixBuf[sel]) cudaFree(ctx->matrixBuf[sel]);
+            if (ctx->dMatrix == ctx->matrixBuf[sel]) ctx->dMatrix = fresh;
+            ctx->matrixBuf[sel] = fresh;
+            ctx->matrixCap[sel] = need;
+            ctx->matrixFoldedUsed[sel] = false;
+        }
+        if (rows > ctx->durCap[sel]) {
+            float* fresh = nullptr;
+            CK(cudaMalloc((void**)&fresh, (size_t)rows * 4));
+            if (ctx->durBuf[sel]) cudaFree(ctx->durBuf[sel]);
+            ctx->durBuf[sel] = fresh;
+            ctx->durCap[sel] = rows;
+        }
+    }
+    return UVRT_OK;
+}
+
 int uvrt_matrix_begin(uvrt_ctx* ctx, int rows)
 {
     if (!ctx) return UVRT_ERR_INVALID;

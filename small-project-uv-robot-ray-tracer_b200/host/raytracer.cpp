@@ -139,6 +139,13 @@ void RayTracer::PlanShardsLPT(const double* launchCost, int launches, int ranks,
 void RayTracer::PlanShards()
 {
     shardPlan.clear();
+    // sharded runs: both count-matrix buffers at their final size now, not in the middle of the run
+    if (ok && shardCount > 1 && mesh) {
+        const long long L = (long long)lightPositions.size();
+        const long long launches = L * (maxIterations > 0 ? maxIterations : 1);
+        const long long rows = launches < MaxWindowRows() ? launches : MaxWindowRows();
+        if (rows > 0) Check(uvrt_matrix_reserve(ctx, (int)rows), "matrix_reserve");
+    }
     if (!ok || shardCount <= 1 || shardParts > 0 || !costAwareSharding || lightPositions.empty() || !mesh) return;
     const size_t L = lightPositions.size();
     std::vector<float> key;

@@ -1034,3 +1034,27 @@ def test_cost_probe_is_deterministic_and_tracks_the_oracle_counters(uv, ctx, roo
         costs.append(44 * a[0] + 75 * a[1])
     other.close()
     assert max(costs) / min(costs) > 1.1
+
+
+def test_timeline_log_of_a_run(uv, room, tmp_path):
+    """The "timeline" option (tracing): every C-ABI call with its host time and every stage launch with
+    its enqueue time and device start/stop, as JSON; NVTX ranges ride on the same scopes."""
+    import json
+    sim = uv.Sim(asset_root=T.DATA)
+    sim.load_mesh("testroomopt")
+    sim.init("route")
+    sim.set_params(photonCount=1 << 21, maxIterations=1)
+    c = sim.ctx
+    c.set_option("timeline", 1)
+    sim.run()
+    path = tmp_path / "timeline.json"
+    c.timeline_dump(path)
+    c.set_option("timeline", 0)
+    t = json.load(open(path))
+    names = [k[0] for k in t["kernels"]]
+    assert names.count("extend") == 12 and names.count("generate") == 12 and "computeDosage" in names and "reset" in names
+    for name, host_us, start_us, stop_us in t["kernels"]:
+        assert stop_us >= start_us >= 0 and host_us >= 0
+    calls = [k[0] for k in t["calls"]]
+    assert calls.count("uvrt_trace") == 12 and "uvrt_reset" in calls and "uvrt_read" in calls
+    sim.close()
