@@ -88,12 +88,9 @@ def main():
     for it in range(1, args.iterations + 1):
         sim.tick()
         if it in stops:
+            if world > 1:
+                sim.reduce()          # folds the pending rows of the count matrix (one all-reduce): every rank holds the complete map
             local_sum = ctx.read(uv.BUF.SUM)
-            if dist is not None:
-                import torch
-                t = torch.from_numpy(local_sum).cuda()
-                dist.all_reduce(t)
-                local_sum = t.cpu().numpy()
             per_light = it * int(p.photonsPerLight)           # photonMapSize / L after `it` iterations
             with np.errstate(divide="ignore", invalid="ignore"):
                 maps[it] = np.float64(p.lightIntensity) * 0.1 * local_sum / (area * per_light)
