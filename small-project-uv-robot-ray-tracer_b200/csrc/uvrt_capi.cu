@@ -7,6 +7,9 @@
 #include "uvrt_bvh_build.cuh"
 #include "uvrt_scene_prep.cuh"
 #include "uvrt_fast.cuh"
+#ifdef UVRT_EXPERIMENTS
+#include "uvrt_fast_refill.cuh"
+#endif
 
 #include <dlfcn.h>
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler injects itself
@@ -100,6 +103,13 @@ struct RaySlot {
     bool binExtentKnown = false;
     cudaEvent_t genDone = nullptr, freeEv = nullptr;
     bool inFlight = false;               // freeEv has been recorded at least once
+#ifdef UVRT_EXPERIMENTS
+    // lists of the refill extend ("fast_cfg" 2, uvrt_fast_refill.cuh): counters, winners to verify, rays to re-trace
+    RefillCtl* dRefillCtl = nullptr;
+    uint4* dVerify = nullptr;
+    uint32_t* dRetry = nullptr;
+    long long refillCap = 0;
+#endif
 };
 
 struct uvrt_ctx {
@@ -121,7 +131,15 @@ struct uvrt_ctx {
     FastGrid* dFastGrid = nullptr;
     FastStats* dFastStats = nullptr;
     int fastCheck = 0;                   // option "fast_check": trace every ray twice and count certified mismatches
-    int fastCfg = 0;                     // option "fast_cfg": register budget of the fast kernel
+    int fastCfg = 0;                     // option "fast_cfg": register budget of the fast kernel (experiments: 2 = refill kernel)
+#ifdef UVRT_EXPERIMENTS
+    FastGrid fastGridHost{};             // copy of *dFastGrid (kernel argument of the refill extend)
+    uint4* dQPairsSel = nullptr;         // layout 1 of the quantised pairs (refill extend), built on first use
+    size_t qpairSelCap = 0;
+    bool qpairSelValid = false;
+    int refillChunk = 64;                // option "refill_chunk": rays a warp takes from the queue at a time
+    int refillBlocksPerSm = 0;           // resident blocks of k_extend_fast_refill (occupancy query, cached)
+#endif
     cudaTextureObject_t pairsTex = 0;   // the same buffer as a 1-D float4 texture ("fetch_mode" experiment)
     int fetchMode = 3;   // 3: rays, permutation kept out of L1 (ld.global.L1::no_allocate); 0: plain loads; 1/2: texture experiments; 4: + evict_last nodes
     float4* dPairs = nullptr;   // nPairs x 4 float4
@@ -574,6 +592,55 @@ int bin_finish(uvrt_ctx* ctx, long long nRays, cudaStream_t stream)
     return UVRT_OK;
 }
 
+#ifdef UVRT_EXPERIMENTS
+// The refill extend (uvrt_fast_refill.cuh, rejected): persistent conservative traversal, then the certificate for its winners, then the
+// reference-order traversal of what is left.  The lists belong to the ray slot, like the permutation.
+int launch_fast_refill(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
+{
+    RaySlot& S = ctx->rs();
+    cudaStream_t st = ctx->xStream;
+    if (!ctx->qpairSelValid) {
+        if ((size_t)ctx->nPairs > ctx->qpairSelCap) {
+            uint4* fresh = nullptr;
+            CK(cudaMalloc((void**)&fresh, (size_t)ctx->nPairs * 32));
+            if (ctx->dQPairsSel) cudaFree(ctx->dQPairsSel);
+            ctx->dQPairsSel = fresh;
+            ctx->qpairSelCap = (size_t)ctx->nPairs;
+        }
+        k_fast_quantize<<<grid_for(ctx->nPairs, 256), 256, 0, st>>>(ctx->dPairs, ctx->nPairs, ctx->dQPairsSel, ctx->dFastGrid, 1);
+        ctx->launches++;
+        CK_LAUNCH("fast_quantize (layout 1)");
+        ctx->qpairSelValid = true;
+    }
+    if (nRays > S.refillCap) {
+        void* old[] = {S.dRefillCtl, S.dVerify, S.dRetry};
+        for (void* p : old) if (p) cudaFree(p);
+        S.dRefillCtl = nullptr; S.dVerify = nullptr; S.dRetry = nullptr; S.refillCap = 0;
+        const long long cap = S.rayCap > nRays ? S.rayCap : nRays;
+        CK(cudaMalloc((void**)&S.dRefillCtl, sizeof(RefillCtl)));
+        CK(cudaMalloc((void**)&S.dVerify, (size_t)cap * 16));
+        CK(cudaMalloc((void**)&S.dRetry, (size_t)cap * 4));
+        S.refillCap = cap;
+    }
+    if (!ctx->refillBlocksPerSm) {
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_fast_refill<kStack, 128, 8>, 128, 0));
+        ctx->refillBlocksPerSm = nb > 0 ? nb : 1;
+    }
+    CK(cudaMemsetAsync(S.dRefillCtl, 0, sizeof(RefillCtl), st));
+    const int sms = ctx->prop.multiProcessorCount;
+    k_extend_fast_refill<kStack, 128, 8><<<sms * ctx->refillBlocksPerSm, 128, 0, st>>>(
+        ctx->dWtris, S.dRays, ctx->dQPairsSel, ctx->fastGridHost, (uint32_t)nRays, perm, S.dRefillCtl, S.dVerify, S.dRetry,
+        (uint32_t)ctx->refillChunk, ctx->fastCheck, ctx->dFastStats);
+    k_fast_verify<<<sms * 8, 128, 0, st>>>(ctx->xCounts, ctx->dWtris, S.dRays, S.dRefillCtl, S.dVerify, S.dRetry, ctx->dFastStats,
+                                           ctx->fastCheck);
+    k_extend_retry<kStack><<<ctx->fastCheck ? sms * 8 : sms, 128, 0, st>>>(ctx->xCounts, ctx->dWtris, S.dRays, ctx->dPairs, S.dRefillCtl,
+                                                                         S.dRetry, ctx->dFastStats);
+    ctx->launches += 2;
+    return UVRT_OK;
+}
+#endif
+
 int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 {
     int v = ctx->extendVariant < 0 ? default_variant(ctx) : ctx->extendVariant;
@@ -596,6 +663,12 @@ int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
         ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->dQPairs, ctx->dFastGrid, (uint32_t)nRays, perm, ctx->dFastStats, ctx->fastCheck)
             // "fast_cfg": 0 = 128 threads, at most 48 registers (47 used; 40 resident warps per SM; the default),
             // 1 = at most 64 registers (54 used; 32 warps).  (64-thread blocks: the same; 256-thread blocks: 2.5 % slower.)
+#ifdef UVRT_EXPERIMENTS
+            if (ctx->fastCfg == 2) {
+                int rc = launch_fast_refill(ctx, nRays, perm);
+                if (rc) return rc;
+            } else
+#endif
             if (ctx->fastCfg == 1) UVRT_FAST_LAUNCH(128, 8);
             else UVRT_FAST_LAUNCH(128, 10);
 #undef UVRT_FAST_LAUNCH
@@ -730,6 +803,13 @@ void uvrt_destroy(uvrt_ctx* ctx)
     if (ctx->accStream) { cudaStreamSynchronize(ctx->accStream); cudaStreamDestroy(ctx->accStream); }
     if (ctx->dCountsAlt) cudaFree(ctx->dCountsAlt);
     if (ctx->dQPairs) cudaFree(ctx->dQPairs);
+#ifdef UVRT_EXPERIMENTS
+    if (ctx->dQPairsSel) cudaFree(ctx->dQPairsSel);
+    for (RaySlot& r : ctx->slots) {
+        void* q[] = {r.dRefillCtl, r.dVerify, r.dRetry};
+        for (void* p : q) if (p) cudaFree(p);
+    }
+#endif
     if (ctx->dFastGrid) cudaFree(ctx->dFastGrid);
     if (ctx->dFastStats) cudaFree(ctx->dFastStats);
     for (int k = 0; k < 2; k++) {
@@ -1205,9 +1285,13 @@ static int fast_prepare(uvrt_ctx* ctx)
         CK(cudaMalloc((void**)&ctx->dFastStats, sizeof(FastStats)));
         CK(cudaMemsetAsync(ctx->dFastStats, 0, sizeof(FastStats), ctx->stream));
     }
-    k_fast_quantize<<<grid_for(ctx->nPairs, 256), 256, 0, ctx->stream>>>(ctx->dPairs, ctx->nPairs, ctx->dQPairs, ctx->dFastGrid);
+    k_fast_quantize<<<grid_for(ctx->nPairs, 256), 256, 0, ctx->stream>>>(ctx->dPairs, ctx->nPairs, ctx->dQPairs, ctx->dFastGrid, 0);
     ctx->launches++;
     CK_LAUNCH("fast_quantize");
+#ifdef UVRT_EXPERIMENTS
+    CK(cudaMemcpyAsync(&ctx->fastGridHost, ctx->dFastGrid, sizeof(FastGrid), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->qpairSelValid = false;
+#endif
     CK(cudaStreamSynchronize(ctx->stream));
     return UVRT_OK;
 }
@@ -2034,7 +2118,22 @@ int uvrt_set_option(uvrt_ctx* ctx, const char* key, int value)
         }
     }
     else if (!strcmp(key, "fast_check")) ctx->fastCheck = value;
-    else if (!strcmp(key, "fast_cfg")) ctx->fastCfg = value;
+    else if (!strcmp(key, "fast_cfg")) {
+#ifdef UVRT_EXPERIMENTS
+        const int hi = 2;
+#else
+        const int hi = 1;
+#endif
+        if (value < 0 || value > hi)
+            return fail(ctx, UVRT_ERR_INVALID, "fast_cfg must be 0 or 1 (2, the refill kernel, exists only in builds with -DUVRT_EXPERIMENTS)");
+        ctx->fastCfg = value;
+    }
+#ifdef UVRT_EXPERIMENTS
+    else if (!strcmp(key, "refill_chunk")) {
+        if (value < 1 || value > 65536) return fail(ctx, UVRT_ERR_INVALID, "refill_chunk must be in 1..65536");
+        ctx->refillChunk = value;
+    }
+#endif
     else if (!strcmp(key, "hist_mode")) ctx->histMode = value;
     else if (!strcmp(key, "blocks_per_sm")) ctx->blocksPerSm = value;
     else if (!strcmp(key, "refill")) ctx->refill = value;
@@ -2076,6 +2175,9 @@ int uvrt_get_option(uvrt_ctx* ctx, const char* key, int* value)
     else if (!strcmp(key, "fast_ready")) *value = fast_usable(ctx) ? 1 : 0;
     else if (!strcmp(key, "fast_check")) *value = ctx->fastCheck;
     else if (!strcmp(key, "fast_cfg")) *value = ctx->fastCfg;
+#ifdef UVRT_EXPERIMENTS
+    else if (!strcmp(key, "refill_chunk")) *value = ctx->refillChunk;
+#endif
     else if (!strcmp(key, "experiments")) {
 #ifdef UVRT_EXPERIMENTS
         *value = 1;

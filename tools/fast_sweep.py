@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--variants", default="2,50")
+    ap.add_argument("--cfgs", default="0,1", help='"fast_cfg" values of variant 50: 0 / 1 register budgets, 2 = refill kernel (make EXPERIMENTS=1 builds only)')
+    ap.add_argument("--chunks", default="64", help='"refill_chunk" values (fast_cfg 2 only)')
     args = ap.parse_args()
     f32 = np.float32
     if args.scene == "room":
@@ -56,9 +58,14 @@ def main():
         lp = lamps[pi]
         ref = None
         for v in [int(x) for x in args.variants.split(",")]:
-            for cfg in ((0, 1) if v >= 50 else (0,)):
+            cfgs = [(int(x), 0) for x in args.cfgs.split(",") if int(x) != 2] if v >= 50 else [(0, 0)]
+            if v >= 50 and "2" in args.cfgs.split(","):
+                cfgs += [(2, int(x)) for x in args.chunks.split(",")]
+            for cfg, chunk in cfgs:
                 c.set_option("extend_variant", v)
                 c.set_option("fast_cfg", cfg)
+                if chunk:
+                    c.set_option("refill_chunk", chunk)
                 c.set_option("fast_check", 0)
                 c.fast_stats(reset=True)
                 times = []
@@ -77,10 +84,10 @@ def main():
                 if ref is None:
                     ref = (rays, counts)
                 bad = int(np.count_nonzero((rays["dist"].view(np.uint32) != ref[0]["dist"].view(np.uint32)) | (rays["triID"] != ref[0]["triID"])))
-                out = {"scene": args.scene, "pos": pi, "variant": v, "fast_cfg": cfg, "ms_best": round(min(times), 4), "ms_med": round(float(np.median(times)), 4),
+                out = {"scene": args.scene, "pos": pi, "variant": v, "fast_cfg": cfg, "refill_chunk": chunk, "ms_best": round(min(times), 4), "ms_med": round(float(np.median(times)), 4),
                        "mrays_s": round(P / min(times) / 1e3, 1), "rays_differ": bad, "counts_equal": bool(np.array_equal(counts, ref[1])),
                        "cert_fallbacks_per_launch": st["cert_fallbacks"] // (args.reps + 2), "ineligible_per_launch": st["ineligible"] // (args.reps + 2)}
-                if args.check and v >= 50 and cfg == 0:
+                if args.check and v >= 50 and cfg in (0, 2):
                     c.set_option("fast_check", 1)
                     c.reset(False)
                     c.generate(lp, length, 0, P, 7 * pi)
