@@ -661,8 +661,8 @@ int launch_extend(uvrt_ctx* ctx, long long nRays, const uint32_t* perm)
 #define UVRT_FAST_LAUNCH(THREADS, MINB)                                                                                  \
     k_extend_fast<kStack, THREADS, MINB><<<grid_for(nRays, THREADS), THREADS, 0, ctx->xStream>>>(                          \
         ctx->xCounts, ctx->dWtris, ctx->rs().dRays, ctx->dPairs, ctx->dQPairs, ctx->dFastGrid, (uint32_t)nRays, perm, ctx->dFastStats, ctx->fastCheck)
-            // "fast_cfg": 0 = 128 threads, at most 48 registers (47 used; 40 resident warps per SM; the default),
-            // 1 = at most 64 registers (54 used; 32 warps).  (64-thread blocks: the same; 256-thread blocks: 2.5 % slower.)
+            // "fast_cfg": 0 = 128 threads, at most 48 registers (46 used; 40 resident warps per SM; the default),
+            // 1 = at most 64 registers (50 used; 32 warps).  (64-thread blocks: the same; 256-thread blocks: 2.5 % slower.)
 #ifdef UVRT_EXPERIMENTS
             if (ctx->fastCfg == 2) {
                 int rc = launch_fast_refill(ctx, nRays, perm);
