@@ -35,8 +35,9 @@ class Stats(C.Structure):
 
 
 def lab():
-    so = "/tmp/liblab.so"
     src = os.path.join(ROOT, "tools", "traversal_lab.c")
+    os.makedirs(os.path.join(ROOT, "tools", "_build"), exist_ok=True)
+    so = os.path.join(ROOT, "tools", "_build", "liblab.so")
     if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.run(["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", so, "-lm"], check=True)
     L = C.CDLL(so)
