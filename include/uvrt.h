@@ -183,9 +183,13 @@ int uvrt_matrix_fold(uvrt_ctx* ctx, const float* durations, int rows, int reduce
  *                     rays without a certificate re-traced in reference order -- same bits as 0/1/2).  -1 (default)
  *                     is 50 wherever it can serve the scene (tame, nested boxes; uvrt_get_option "fast_ready"), else 2.
  *                     "fast_check" = 1 traces every ray both ways and counts disagreements (uvrt_fast_stats),
- *                     "fast_cfg" selects the register budget; read only: "scene_nested", "fast_ready".  Builds with -DUVRT_EXPERIMENTS (`make EXPERIMENTS=1`, read-only option
- *                     "experiments") also carry the rejected variants of profiles/r1_sweeps.md: 10..24 persistent
- *                     warps with a global queue, 40..43 chunk-persistent warps
+ *                     "fast_cfg" selects the register budget (0: 48, the default; 1: 64); read only:
+ *                     "scene_nested", "fast_ready".  Builds with -DUVRT_EXPERIMENTS (`make EXPERIMENTS=1`, read-only
+ *                     option "experiments") also carry the rejected variants of profiles/r1_sweeps.md and
+ *                     profiles/r2_fast_extend.md: 10..24 persistent warps with a global queue, 40..43 chunk-persistent
+ *                     warps, and "fast_cfg" 2, the refill variant of the fast extend ("refill_chunk": rays per chunk)
+ *   "timeline"        1: log the host time of every call and the device start / stop of every stage launch
+ *                     (uvrt_timeline_dump)
  *   "bin_rays"        1 (default): counting sort of the ray queue by direction / origin cell before extend;
  *                     "bin_y", "bin_t", "bin_p": the bin grid
  *   "pipeline"        1 (default): generate + bin of launch k+1 on a second stream next to extend k
