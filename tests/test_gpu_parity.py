@@ -587,7 +587,8 @@ def test_full_default_run_bookkeeping(uv, room):
     beyond what the oracle traces in seconds -- checked through properties that do not depend on size:
     the maps the RayTracer run leaves behind equal, bit for bit, the f64 sums / maxima formed on the host
     from per-launch integer counts (same SEED chain, launched one by one through the stage API); every
-    ray that reports a hit was counted exactly once; the dose inverts back to the photon map."""
+    ray that reports a hit was counted exactly once; the dose inverts back to the photon map.
+    (The same run against the golden of the reference's own compiled sources: test_default_run_matches_reference_golden.)"""
     tris, nodes, tri_idx, floor = room
     sim = uv.Sim(asset_root=T.DATA)
     sim.load_mesh("testroomopt")
