@@ -1,6 +1,6 @@
-"""The certified fast extend (variants 50 / 51) against the exact kernel (variant 2): time, results, fallbacks.
+"""The certified fast extend (variant 50) against the exact kernel (variant 2): time, results, fallbacks.
 
-    python tools/fast_sweep.py [--scene room|soup1m|soup10m] [--rays N] [--positions 0,5,11] [--check]
+    python tools/fast_sweep.py [--scene room|soup1m|soup10m] [--rays N] [--positions 0,5,11] [--cfgs 0,1] [--chunks 64] [--check]
 
 Per lamp position: one launch generated on the device, then bin + extend timed (CUDA events, best of 5) for every
 variant / register budget; the ray records (dist bits, triID) and the count vector must be byte-identical to variant 2's.
